@@ -1,0 +1,206 @@
+/*
+ * imk.h -- C ABI of the B200-native Inconsistency-Mask pseudo-labelling hot path.
+ *
+ * The reference (MichaelVorndran/InconsistencyMasks) is pure Python and has no FFI
+ * of its own; the boundary this library sits behind is the set of Python helpers
+ * in the reference's functions.py.  Every entry point below names the reference
+ * interface it replaces (file:line relative to the reference repository root).
+ * inconsistencymasks_b200/functions.py binds these symbols with ctypes and keeps
+ * the reference's helper names / argument meaning; INTEGRATION.md shows the stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions across the boundary.
+ *   - every function returns 0 on success, a negative IMK_E* code otherwise;
+ *     imk_last_error() returns a thread-local description of the last failure.
+ *   - the caller owns every buffer passed in.  Pointers named *_dev are CUDA
+ *     device pointers on the current device, *_host are host pointers (pinned
+ *     memory gives asynchronous copies; pageable works but serialises).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Device-buffer calls are asynchronous on that stream; *_host calls return
+ *     after their results are in the host buffers.
+ *   - layouts follow the reference: images uint8 NHWC [N,H,W,c] exactly as
+ *     cv2.imread returns them (BGR on disk order for c == 3), probabilities
+ *     float32 NHWC [N,H,W,K], labels / IM uint8 [N,H,W], sizes int64 [N].
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ *     with IMK_ECUDA.
+ */
+#ifndef IMK_H_
+#define IMK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMK_VERSION 100
+
+#define IMK_OK        0
+#define IMK_EINVAL   -1   /* bad argument (shape, NULL pointer, unsupported K / M) */
+#define IMK_ECUDA    -2   /* a CUDA runtime call or kernel launch failed          */
+#define IMK_ENOMEM   -3   /* device or host allocation failed                     */
+#define IMK_ESTATE   -4   /* handle used in a way its state does not allow        */
+
+#define IMK_ACT_SIGMOID 0   /* config.ini ACTIFU_OUTPUT = sigmoid (ISIC_2018, HELA) */
+#define IMK_ACT_SOFTMAX 1   /* config.ini ACTIFU_OUTPUT = softmax (SUIM, CITYSCAPES) */
+
+#define IMK_IN_U8   0       /* model.predict on the uint8 array of functions.py:2852 */
+#define IMK_IN_F32  1       /* model.predict on a float32 array (benchmark_hela, functions.py:1199) */
+
+#define IMK_MAX_MODELS 16
+#define IMK_MAX_CLASSES 256
+
+int         imk_version(void);
+const char *imk_last_error(void);
+/* Number of kernel launches this thread issued through the library so far. */
+int64_t     imk_launch_count(void);
+/* 1 when a CUDA device is usable from this process, else 0 (never throws). */
+int         imk_device_available(void);
+
+/* ------------------------------------------------------------------------- *
+ *  Row a5 / a6 : pred_masks_to_im_binary  (functions.py:3104-3120)
+ *                pred_masks_to_im_multiclass (functions.py:3123-3137)
+ *  masks_dev: int64 [M, P] (P = pixels of ONE image), any integer values --
+ *  the binary helper is a SUM over models, the multiclass one an all-equal test.
+ *  Outputs: label/im uint8 [P]; sizes_dev int64 [2] = {im_size, pred_size}
+ *  (multiclass writes im_size only).
+ * ------------------------------------------------------------------------- */
+int imk_masks_to_im_binary(const int64_t *masks_dev, int M, int64_t P,
+                           uint8_t *label_dev, uint8_t *im_dev, int64_t *sizes_dev,
+                           void *stream);
+int imk_masks_to_im_multiclass(const int64_t *masks_dev, int M, int64_t P,
+                               uint8_t *label_dev, uint8_t *im_dev, int64_t *sizes_dev,
+                               void *stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Rows a2 / a3 + a7 / a9 : get_im_prediction_binary (functions.py:3140-3162),
+ *  get_im_prediction_hela (functions.py:3165-3202) with model.predict replaced
+ *  by its output, fused with the blanking of functions.py:2867-2874 / 2968-2974.
+ *
+ *  probs_dev   host array of M device pointers, each float32 [N,H,W,K], K = 1 (ISIC)
+ *              or 3 (HeLa heads alive, dead, position).
+ *  strict_gt   1: prob >  thr (functions.py:3157)   0: prob >= thr (functions.py:3187-3189)
+ *  img_dev     uint8 [N,H,W,c] to blank (may be NULL when block_in == 0 or img_out_dev == NULL)
+ *  labels_dev  uint8 [K][N,H,W] (head-major planes): 255 where all models fire
+ *  im_dev      uint8 [N,H,W]: 255 where models disagree (K == 3: max over heads)
+ *  im_size_dev int64 [N]: K == 1 pixels of the IM; K == 3 the SUM of the three head
+ *              IM sizes (functions.py:3200), counted before blanking
+ *  pred_size_dev int64 [K][N] or NULL: pixels where all models fire
+ *  block_in    write img_out = im ? 0 : img          block_out: label = im ? 0 : label
+ *              (K == 1: a no-op without morphology, the label is already 0 there;
+ *              K == 3: clears alive / dead where ANY head disagrees, functions.py:2972-2973;
+ *              head 2 (position) is always returned raw -- the reference blanks the circle
+ *              image the host draws from it, functions.py:2953-2965, 2974)
+ * ------------------------------------------------------------------------- */
+int imk_im_binary(const float *const *probs_dev, int M, int64_t N, int H, int W, int K,
+                  float thr, int strict_gt,
+                  const uint8_t *img_dev, int c, int block_in, int block_out,
+                  uint8_t *img_out_dev, uint8_t *labels_dev, uint8_t *im_dev,
+                  int64_t *im_size_dev, int64_t *pred_size_dev, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Rows a4 + a8 : get_im_prediction_multiclass (functions.py:3206-3238) fused with
+ *  the blanking of functions.py:3054-3061.  argmax = first index of the maximum,
+ *  NaN counts as the maximum (np.argmax, functions.py:3225).
+ *  label_dev   uint8 [N,H,W] class id where all models agree else 0
+ *  im_dev      uint8 [N,H,W] 255 where they do not
+ *  lists_equal_dev uint8 [N] or NULL: 1 when every model predicts the same SET of
+ *              classes over the image (functions.py:3226-3234); needs K <= 64.
+ * ------------------------------------------------------------------------- */
+int imk_im_multiclass(const float *const *probs_dev, int M, int64_t N, int H, int W, int K,
+                      const uint8_t *img_dev, int c, int block_in, int block_out,
+                      uint8_t *img_out_dev, uint8_t *label_dev, uint8_t *im_dev,
+                      int64_t *im_size_dev, uint8_t *lists_equal_dev, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Optional morphology of rows a7-a9 (off in config.ini: ERODE_KERNEL = DILATE_KERNEL = 0).
+ *  cv2.erode / cv2.dilate(mask, ones((k,k)), iterations=1) on uint8 [N,H,W]
+ *  (functions.py:2858-2864); dilate_mask == 3x3 dilate of the label map
+ *  (functions.py:3075-3100).  src and dst must not alias.
+ * ------------------------------------------------------------------------- */
+int imk_erode_u8(const uint8_t *src_dev, uint8_t *dst_dev, int64_t N, int H, int W, int k, void *stream);
+int imk_dilate_u8(const uint8_t *src_dev, uint8_t *dst_dev, int64_t N, int H, int W, int k, void *stream);
+/* image[im > 0] = 0 over c channels and n_labels label planes [n_labels][N,H,W]
+ * (functions.py:2867-2874, 2968-2974, 3054-3061).  In place.  Either may be NULL. */
+int imk_blank(const uint8_t *im_dev, int64_t N, int H, int W,
+              uint8_t *img_dev, int c, uint8_t *labels_dev, int n_labels, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Row a1 : get_unet (unet.py:46-67) forward, i.e. model.predict
+ *  (functions.py:3157, 3184, 3224).
+ *
+ *  weights: the 104 float32 arrays of Keras model.get_weights() in creation order
+ *  (conv kernel HWIO + bias; BatchNormalization gamma, beta, moving_mean,
+ *  moving_variance), SURVEY.md appendix C.  Host pointers; copied and repacked.
+ * ------------------------------------------------------------------------- */
+typedef struct imk_unet imk_unet_t;
+
+typedef struct imk_unet_desc {
+    int   height, width;      /* unet.py:47 i_height, i_width (multiples of 16)        */
+    int   in_channels;        /* i_channels: 1 or 3                                     */
+    int   num_outputmasks;    /* K                                                      */
+    float alpha;              /* width multiplier, channels = int(k * alpha)            */
+    int   ks;                 /* 3 (unet.py:46 default; 1 and 3 supported)              */
+    int   act_out;            /* IMK_ACT_SIGMOID / IMK_ACT_SOFTMAX                      */
+    int   swap_rb;            /* 1: feed channel 2-i of the image buffer (the reference
+                                 feeds cvtColor(BGR2RGB) of the array it later blanks,
+                                 functions.py:2846-2852); 0: feed as is                 */
+} imk_unet_desc;
+
+int  imk_unet_create(const imk_unet_desc *desc, const float *const *weights_host,
+                     const int64_t *weight_sizes, int n_weights, imk_unet_t **out);
+void imk_unet_destroy(imk_unet_t *net);
+int  imk_unet_param_count(const imk_unet_t *net, int64_t *count);
+/* Selects the convolution engine for the layers that have a tensor-core path:
+ * 0 = shared-memory-tiled direct convolutions everywhere, 1 = tcgen05 implicit GEMM
+ * where Cin is wide enough (default).  Both are CUDA; used for A/B measurements. */
+int  imk_unet_set_engine(imk_unet_t *net, int engine);
+/* Changes desc.swap_rb after creation (the same weights serve get_im_prediction_*, which
+ * receive the RGB array, and create_pseudo_labels_im_*, which hold the BGR one). */
+int  imk_unet_set_swap_rb(imk_unet_t *net, int swap_rb);
+
+/* probs_dev float32 [N,H,W,K].  images_dev: uint8 or float32 [N,H,W,c] per in_dtype. */
+int imk_unet_forward(imk_unet_t *net, const void *images_dev, int in_dtype, int64_t N,
+                     float *probs_dev, void *stream);
+/* Same with host buffers (what model.predict does): copies in, runs, copies out. */
+int imk_unet_predict_host(imk_unet_t *net, const void *images_host, int in_dtype, int64_t N,
+                          float *probs_host);
+
+/* ------------------------------------------------------------------------- *
+ *  Fused fast path: ensemble forward + a2/a3/a4 + a7/a8/a9 with the fp32
+ *  probability maps never written to HBM.  Same outputs as imk_im_binary /
+ *  imk_im_multiclass fed with imk_unet_forward's probabilities, bit for bit.
+ *  All models must share height, width, in_channels, num_outputmasks, act_out.
+ * ------------------------------------------------------------------------- */
+int imk_ensemble_im_binary(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+                           float thr, int strict_gt, int block_in, int block_out,
+                           uint8_t *img_out_dev, uint8_t *labels_dev, uint8_t *im_dev,
+                           int64_t *im_size_dev, int64_t *pred_size_dev, void *stream);
+int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+                               int block_in, int block_out,
+                               uint8_t *img_out_dev, uint8_t *label_dev, uint8_t *im_dev,
+                               int64_t *im_size_dev, uint8_t *lists_equal_dev, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ *  The per-directory loops of create_pseudo_labels_im_ISIC_2018 / _hela /
+ *  _multiclass (functions.py:2844-2887, 2932-2980, 3020-3066) minus PNG I/O, on
+ *  HOST buffers: images are streamed to the device in chunks on two streams so
+ *  that copies overlap compute, results are streamed back.  erode_kernel ==
+ *  dilate_kernel == 0 only (the config.ini defaults); use the device-buffer calls
+ *  for morphology.  Outputs as in the device calls above; any output may be NULL.
+ * ------------------------------------------------------------------------- */
+int imk_pseudo_label_binary_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+                                 float thr, int strict_gt, int block_in, int block_out,
+                                 uint8_t *img_out_host, uint8_t *labels_host, uint8_t *im_host,
+                                 int64_t *im_size_host, int64_t *pred_size_host, int64_t chunk);
+int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+                                     int block_in, int block_out,
+                                     uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_host,
+                                     int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMK_H_ */

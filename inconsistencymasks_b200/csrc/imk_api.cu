@@ -1,0 +1,154 @@
+// Library-wide plumbing of the C ABI (include/imk.h): error reporting, launch
+// accounting, device probing, and the host-buffer pipelines that stand in for the
+// per-directory loops of create_pseudo_labels_im_* (functions.py:2844-2887,
+// 2932-2980, 3020-3066) minus PNG I/O.
+#include <stdarg.h>
+#include <algorithm>
+#include "imk_unet.cuh"
+
+namespace imk {
+
+static thread_local char g_err[1024] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int64_t &launch_counter() { return g_launches; }
+
+}  // namespace imk
+
+using namespace imk;
+
+extern "C" int imk_version(void) { return IMK_VERSION; }
+extern "C" const char *imk_last_error(void) { return g_err; }
+extern "C" int64_t imk_launch_count(void) { return g_launches; }
+
+extern "C" int imk_device_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n > 0 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+//  Host-buffer pipeline.  Two slots, each with its own stream and device buffers:
+//  slot s uploads chunk i+1 while slot s^1 computes chunk i and downloads chunk i-1's
+//  results -- copies run on the copy engines concurrently with the kernels.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint8_t *img = nullptr, *img_out = nullptr, *labels = nullptr, *im = nullptr;
+    int64_t *im_size = nullptr, *pred_size = nullptr;
+    uint8_t *lists_equal = nullptr;
+};
+
+struct Pipeline {
+    Slot slot[2];
+    int64_t chunk = 0;
+    size_t img_bytes = 0;
+    int planes = 0;
+    ~Pipeline() {
+        for (Slot &s : slot) {
+            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+            cudaFree(s.img); cudaFree(s.img_out); cudaFree(s.labels); cudaFree(s.im);
+            cudaFree(s.im_size); cudaFree(s.pred_size); cudaFree(s.lists_equal);
+        }
+    }
+};
+
+int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images, int64_t N,
+                      float thr, int strict, int block_in, int block_out,
+                      uint8_t *img_out, uint8_t *labels, uint8_t *im, int64_t *im_size, int64_t *pred_size,
+                      uint8_t *lists_equal, int64_t chunk, const char *who) {
+    IMK_REQUIRE(nets && M >= 1 && nets[0], "%s: no models", who);
+    IMK_REQUIRE(images && N >= 0, "%s: NULL images or N < 0", who);
+    if (N == 0) return IMK_OK;
+    const imk_unet_desc &d = nets[0]->desc;
+    const int64_t HW = (int64_t)d.height * d.width;
+    const int K = d.num_outputmasks;
+    const int planes = multiclass ? 1 : K;
+    if (chunk <= 0) chunk = kMaxChunk;
+    chunk = std::min<int64_t>(chunk, N);
+    // Each model keeps ONE workspace, so the two slots serialise on the compute stream
+    // order: kernels of consecutive chunks are issued to a single compute stream while the
+    // uploads / downloads run on the slot streams, ordered by events.
+    Pipeline P;
+    P.chunk = chunk;
+    cudaStream_t compute = nullptr;
+    IMK_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    struct ComputeGuard { cudaStream_t s; ~ComputeGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } guard{compute};
+    cudaEvent_t up_done[2], comp_done[2], down_done[2];
+    for (int s = 0; s < 2; ++s) {
+        IMK_CUDA(cudaStreamCreateWithFlags(&P.slot[s].stream, cudaStreamNonBlocking));
+        IMK_CUDA(cudaMalloc(&P.slot[s].img, (size_t)chunk * HW * d.in_channels));
+        IMK_CUDA(cudaMalloc(&P.slot[s].img_out, (size_t)chunk * HW * d.in_channels));
+        IMK_CUDA(cudaMalloc(&P.slot[s].labels, (size_t)chunk * HW * planes));
+        IMK_CUDA(cudaMalloc(&P.slot[s].im, (size_t)chunk * HW));
+        IMK_CUDA(cudaMalloc(&P.slot[s].im_size, sizeof(int64_t) * chunk));
+        IMK_CUDA(cudaMalloc(&P.slot[s].pred_size, sizeof(int64_t) * chunk * planes));
+        IMK_CUDA(cudaMalloc(&P.slot[s].lists_equal, (size_t)chunk));
+        IMK_CUDA(cudaEventCreateWithFlags(&up_done[s], cudaEventDisableTiming));
+        IMK_CUDA(cudaEventCreateWithFlags(&comp_done[s], cudaEventDisableTiming));
+        IMK_CUDA(cudaEventCreateWithFlags(&down_done[s], cudaEventDisableTiming));
+    }
+    struct EvGuard { cudaEvent_t *a, *b, *c; ~EvGuard() { for (int s = 0; s < 2; ++s) { cudaEventDestroy(a[s]); cudaEventDestroy(b[s]); cudaEventDestroy(c[s]); } } } evg{up_done, comp_done, down_done};
+
+    const int64_t n_chunks = (N + chunk - 1) / chunk;
+    int rc = IMK_OK;
+    for (int64_t i = 0; i < n_chunks; ++i) {
+        const int s = (int)(i & 1);
+        Slot &S = P.slot[s];
+        const int64_t n0 = i * chunk, n = std::min<int64_t>(chunk, N - n0);
+        // slot buffers are free again once chunk i-2's download has finished
+        if (i >= 2) IMK_CUDA(cudaStreamWaitEvent(S.stream, down_done[s], 0));
+        IMK_CUDA(cudaMemcpyAsync(S.img, images + n0 * HW * d.in_channels, (size_t)n * HW * d.in_channels, cudaMemcpyHostToDevice, S.stream));
+        IMK_CUDA(cudaEventRecord(up_done[s], S.stream));
+        IMK_CUDA(cudaStreamWaitEvent(compute, up_done[s], 0));
+        if (multiclass)
+            rc = imk_ensemble_im_multiclass(nets, M, S.img, n, block_in, block_out, img_out ? S.img_out : nullptr, S.labels, S.im,
+                                            S.im_size, lists_equal ? S.lists_equal : nullptr, compute);
+        else
+            rc = imk_ensemble_im_binary(nets, M, S.img, n, thr, strict, block_in, block_out, img_out ? S.img_out : nullptr, S.labels,
+                                        S.im, S.im_size, pred_size ? S.pred_size : nullptr, compute);
+        if (rc) return rc;
+        IMK_CUDA(cudaEventRecord(comp_done[s], compute));
+        IMK_CUDA(cudaStreamWaitEvent(S.stream, comp_done[s], 0));
+        if (img_out) IMK_CUDA(cudaMemcpyAsync(img_out + n0 * HW * d.in_channels, S.img_out, (size_t)n * HW * d.in_channels, cudaMemcpyDeviceToHost, S.stream));
+        if (labels)
+            for (int k = 0; k < planes; ++k)     // slot planes are n*HW apart, host planes N*HW apart
+                IMK_CUDA(cudaMemcpyAsync(labels + (int64_t)k * N * HW + n0 * HW, S.labels + (int64_t)k * n * HW, (size_t)n * HW, cudaMemcpyDeviceToHost, S.stream));
+        if (im) IMK_CUDA(cudaMemcpyAsync(im + n0 * HW, S.im, (size_t)n * HW, cudaMemcpyDeviceToHost, S.stream));
+        if (im_size) IMK_CUDA(cudaMemcpyAsync(im_size + n0, S.im_size, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, S.stream));
+        if (pred_size && !multiclass)
+            for (int k = 0; k < planes; ++k)
+                IMK_CUDA(cudaMemcpyAsync(pred_size + (int64_t)k * N + n0, S.pred_size + (int64_t)k * n, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, S.stream));
+        if (lists_equal && multiclass) IMK_CUDA(cudaMemcpyAsync(lists_equal + n0, S.lists_equal, (size_t)n, cudaMemcpyDeviceToHost, S.stream));
+        IMK_CUDA(cudaEventRecord(down_done[s], S.stream));
+    }
+    for (int s = 0; s < 2; ++s) IMK_CUDA(cudaStreamSynchronize(P.slot[s].stream));
+    IMK_CUDA(cudaStreamSynchronize(compute));
+    return IMK_OK;
+}
+
+}  // namespace
+
+extern "C" int imk_pseudo_label_binary_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+                                            float thr, int strict_gt, int block_in, int block_out,
+                                            uint8_t *img_out_host, uint8_t *labels_host, uint8_t *im_host,
+                                            int64_t *im_size_host, int64_t *pred_size_host, int64_t chunk) {
+    return run_host_pipeline(nets, M, false, images_host, N, thr, strict_gt, block_in, block_out, img_out_host, labels_host,
+                             im_host, im_size_host, pred_size_host, nullptr, chunk, "imk_pseudo_label_binary_host");
+}
+
+extern "C" int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+                                                int block_in, int block_out,
+                                                uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_host,
+                                                int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk) {
+    return run_host_pipeline(nets, M, true, images_host, N, 0.f, 1, block_in, block_out, img_out_host, label_host, im_host,
+                             im_size_host, nullptr, lists_equal_host, chunk, "imk_pseudo_label_multiclass_host");
+}

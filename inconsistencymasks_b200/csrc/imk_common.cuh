@@ -1,0 +1,68 @@
+// Shared host/device helpers of libimk (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/imk.h"
+
+namespace imk {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- thread-local error / launch accounting --------------------------------
+void set_error(const char *fmt, ...);
+int64_t &launch_counter();
+
+#define IMK_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            imk::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+                           cudaGetErrorString(e_));                                 \
+            return IMK_ECUDA;                                                       \
+        }                                                                           \
+    } while (0)
+
+#define IMK_REQUIRE(cond, ...)                                                      \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            imk::set_error(__VA_ARGS__);                                            \
+            return IMK_EINVAL;                                                      \
+        }                                                                           \
+    } while (0)
+
+// Call right after a <<<>>> launch.
+#define IMK_LAUNCHED()                                                              \
+    do {                                                                            \
+        ++imk::launch_counter();                                                    \
+        IMK_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+// ---- device helpers ----------------------------------------------------------
+// Streaming 128-bit accesses: every byte of the IM path is touched once, keep it
+// out of L1 (guide: ld.global.nc.L1::no_allocate / st.global.L1::no_allocate).
+__device__ __forceinline__ uint4 ldg_stream(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(void *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// The ONE definition of the output activations, shared by the materialised
+// (.predict) path and the fused ensemble path so that both produce identical bits.
+__device__ __forceinline__ float sigmoid_f32(float x) {
+    return 1.0f / (1.0f + __expf(-x));
+}
+
+}  // namespace imk

@@ -1,0 +1,845 @@
+// U-Net forward (reference unet.py:46-67, i.e. model.predict at functions.py:3157 /
+// 3184 / 3224) and the fused ensemble epilogue.
+//
+// Data layout in HBM: activations fp16 NHWC with channels padded to a multiple of 16
+// (zero in the padding), fp32 accumulation everywhere, one rounding to fp16 per layer
+// output.  The 24 convolutions run as
+//   - first layer  (c -> f16, 1x1, x/255 fused)          : in_conv_kernel       (CUDA cores, HBM-bound)
+//   - hidden 3x3 / 1x1 layers                             : tcgen05 implicit GEMM (imk_conv_tc.cu) or the
+//                                                           shared-memory-tiled direct convolution below
+//   - last layer   (f16 -> K, 1x1) + sigmoid / softmax    : out_probs_kernel (materialised fp32, .predict)
+//                                                           or ensemble_im_kernel (fused with the IM, no fp32 in HBM)
+// Order inside a block is Conv -> ReLU -> BatchNorm (unet.py:6-7, 12-16, 34-41): BN is an
+// affine epilogue AFTER the ReLU and is not folded into the convolution.
+#include <math.h>
+#include <vector>
+#include "imk_im.cuh"
+#include "imk_unet.cuh"
+
+namespace imk {
+
+constexpr float kBnEps = 1e-3f;          // Keras BatchNormalization default epsilon
+
+// =============================================================================
+//  first layer: Lambda(x/255) -> Conv2D 1x1 (c -> C1) + ReLU -> BN        unet.py:4-9
+//  one thread = one pixel x 8 output channels (one 128-bit store)
+// =============================================================================
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+in_conv_kernel(const TIn *__restrict__ img, int c, int swap_rb, const float *__restrict__ w /*[c][cout]*/, int cout,
+               const float *__restrict__ bias, const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
+               __half *__restrict__ out, int cout_p, int64_t total_px) {
+    const int chunks = cout_p / 8;
+    const int64_t total = total_px * chunks;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t px = i / chunks;
+        const int co0 = (int)(i % chunks) * 8;
+        float x[4];
+        for (int ch = 0; ch < c; ++ch) {
+            const int src = (swap_rb && c == 3) ? 2 - ch : ch;
+            x[ch] = __fdiv_rn((float)img[px * c + src], 255.0f);
+        }
+        __align__(16) __half o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int co = co0 + j;
+            float v = 0.f;
+            if (co < cout) {
+                v = bias[co];
+                for (int ch = 0; ch < c; ++ch) v = __fmaf_rn(x[ch], w[ch * cout + co], v);
+                v = fmaxf(v, 0.f);
+                v = __fmaf_rn(v, bn_scale[co], bn_shift[co]);
+            }
+            o[j] = __float2half_rn(v);
+        }
+        *reinterpret_cast<uint4 *>(out + px * cout_p + co0) = *reinterpret_cast<const uint4 *>(o);
+    }
+}
+
+// =============================================================================
+//  hidden layers, direct engine: KS x KS conv (+ optional nearest-upsample-2x + add
+//  prologue, unet.py:32-33) + bias + ReLU (+ BN).  16x16 output pixels x 16 output
+//  channels per CTA, input halo tile and the weight slice staged in shared memory in
+//  chunks of 16 input channels, fp32 accumulation in registers (2 pixels x 16 couts per
+//  thread).
+// =============================================================================
+constexpr int kDT = 16;      // tile edge
+constexpr int kDCo = 16;     // output channels per CTA
+constexpr int kDCi = 16;     // input channels per shared-memory stage
+
+template <int KS>
+__global__ void __launch_bounds__(128)
+conv_direct_kernel(const __half *__restrict__ in, const __half *__restrict__ in_lo,
+                   const __half *__restrict__ wgt /*[KS*KS][cin_p][cout_p]*/,
+                   const float *__restrict__ bias, const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
+                   __half *__restrict__ out, int h, int w, int cin_p, int cout_p, int tiles_x) {
+    constexpr int R = KS / 2;
+    constexpr int TH = kDT + KS - 1;                    // halo tile edge
+    constexpr int PITCH = kDCi / 2 + 1;                 // 32-bit words per pixel (+1: conflict-free)
+    __shared__ uint32_t in_s[TH * TH * PITCH];
+    __shared__ __align__(16) float w_s[KS * KS * kDCi][kDCo];
+
+    const int t = threadIdx.x;
+    const int tx = t & 15, ty = t >> 4;                 // ty in 0..7, rows ty and ty+8
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int x0 = tile_x * kDT, y0 = tile_y * kDT;
+    const int co0 = blockIdx.y * kDCo;
+    const int64_t n = blockIdx.z;
+    const __half *in_n = in + n * (int64_t)h * w * cin_p;
+    const __half *lo_n = in_lo ? in_lo + n * (int64_t)(h / 2) * (w / 2) * cin_p : nullptr;
+
+    float acc0[kDCo], acc1[kDCo];
+#pragma unroll
+    for (int j = 0; j < kDCo; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+    for (int cc = 0; cc < cin_p; cc += kDCi) {
+        __syncthreads();
+        // ---- stage the input halo tile (16 channels) --------------------------------
+        for (int i = t; i < TH * TH * 2; i += 128) {
+            const int half_sel = i & 1;                 // which 8-channel half (one 128-bit load)
+            const int p = i >> 1;
+            const int py = p / TH, pxx = p % TH;
+            const int gy = y0 + py - R, gx = x0 + pxx - R;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+                v = *reinterpret_cast<const uint4 *>(in_n + ((int64_t)gy * w + gx) * cin_p + cc + half_sel * 8);
+                if (lo_n) {
+                    const uint4 u = *reinterpret_cast<const uint4 *>(
+                        lo_n + ((int64_t)(gy >> 1) * (w >> 1) + (gx >> 1)) * cin_p + cc + half_sel * 8);
+                    const __half2 *a = reinterpret_cast<const __half2 *>(&v);
+                    const __half2 *b = reinterpret_cast<const __half2 *>(&u);
+                    uint4 r;
+                    __half2 *ro = reinterpret_cast<__half2 *>(&r);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 fa = __half22float2(a[q]), fb = __half22float2(b[q]);
+                        ro[q] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+                    }
+                    v = r;
+                }
+            }
+            uint32_t *dst = in_s + p * PITCH + half_sel * 4;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        // ---- stage the weight slice [KS*KS][16 ci][16 co] as fp32 -----------------------
+        for (int i = t; i < KS * KS * kDCi * 2; i += 128) {
+            const int half_sel = i & 1;
+            const int row = i >> 1;                     // tap*16 + ci
+            const int tap = row / kDCi, ci = row % kDCi;
+            const uint4 v = *reinterpret_cast<const uint4 *>(wgt + ((int64_t)tap * cin_p + cc + ci) * cout_p + co0 + half_sel * 8);
+            const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(hv[q]);
+                w_s[row][half_sel * 8 + 2 * q] = f.x;
+                w_s[row][half_sel * 8 + 2 * q + 1] = f.y;
+            }
+        }
+        __syncthreads();
+        // ---- accumulate ---------------------------------------------------------------
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll
+            for (int dx = 0; dx < KS; ++dx) {
+                const uint32_t *p0 = in_s + ((ty + dy) * TH + tx + dx) * PITCH;
+                const uint32_t *p1 = in_s + ((ty + 8 + dy) * TH + tx + dx) * PITCH;
+                const int tap = dy * KS + dx;
+#pragma unroll
+                for (int c2 = 0; c2 < kDCi / 2; ++c2) {
+                    const uint32_t u0 = p0[c2], u1 = p1[c2];
+                    const float2 a0 = __half22float2(*reinterpret_cast<const __half2 *>(&u0));
+                    const float2 a1 = __half22float2(*reinterpret_cast<const __half2 *>(&u1));
+                    const float4 *wr0 = reinterpret_cast<const float4 *>(w_s[tap * kDCi + 2 * c2]);
+                    const float4 *wr1 = reinterpret_cast<const float4 *>(w_s[tap * kDCi + 2 * c2 + 1]);
+#pragma unroll
+                    for (int q = 0; q < kDCo / 4; ++q) {
+                        const float4 wa = wr0[q], wb = wr1[q];
+                        acc0[4 * q + 0] = fmaf(a0.x, wa.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(a1.x, wa.x, acc1[4 * q + 0]);
+                        acc0[4 * q + 1] = fmaf(a0.x, wa.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(a1.x, wa.y, acc1[4 * q + 1]);
+                        acc0[4 * q + 2] = fmaf(a0.x, wa.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(a1.x, wa.z, acc1[4 * q + 2]);
+                        acc0[4 * q + 3] = fmaf(a0.x, wa.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(a1.x, wa.w, acc1[4 * q + 3]);
+                        acc0[4 * q + 0] = fmaf(a0.y, wb.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(a1.y, wb.x, acc1[4 * q + 0]);
+                        acc0[4 * q + 1] = fmaf(a0.y, wb.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(a1.y, wb.y, acc1[4 * q + 1]);
+                        acc0[4 * q + 2] = fmaf(a0.y, wb.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(a1.y, wb.z, acc1[4 * q + 2]);
+                        acc0[4 * q + 3] = fmaf(a0.y, wb.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(a1.y, wb.w, acc1[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- epilogue: + bias, ReLU, BN affine, one rounding to fp16 -----------------------
+    auto store = [&](const float *acc, int gy, int gx) {
+        if (gy >= h || gx >= w) return;
+        __align__(16) __half o[kDCo];
+#pragma unroll
+        for (int j = 0; j < kDCo; ++j) {
+            float v = fmaxf(acc[j] + bias[co0 + j], 0.f);
+            if (bn_scale) v = __fmaf_rn(v, bn_scale[co0 + j], bn_shift[co0 + j]);
+            o[j] = __float2half_rn(v);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (n * (int64_t)h * w + (int64_t)gy * w + gx) * cout_p + co0);
+        dst[0] = reinterpret_cast<const uint4 *>(o)[0];
+        dst[1] = reinterpret_cast<const uint4 *>(o)[1];
+    };
+    store(acc0, y0 + ty, x0 + tx);
+    store(acc1, y0 + ty + 8, x0 + tx);
+}
+
+// MaxPooling2D((2,2)) on fp16 NHWC  (unet.py:17); one thread = one output pixel x 8 channels
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const __half *__restrict__ in, __half *__restrict__ out, int64_t n, int h, int w, int cp) {
+    const int ho = h / 2, wo = w / 2, chunks = cp / 8;
+    const int64_t total = n * ho * wo * chunks;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int ch = (int)(i % chunks) * 8;
+        int64_t r = i / chunks;
+        const int xo = (int)(r % wo); r /= wo;
+        const int yo = (int)(r % ho);
+        const int64_t img = r / ho;
+        const __half *base = in + ((img * h + 2 * yo) * (int64_t)w + 2 * xo) * cp + ch;
+        const uint4 a = *reinterpret_cast<const uint4 *>(base);
+        const uint4 b = *reinterpret_cast<const uint4 *>(base + cp);
+        const uint4 c = *reinterpret_cast<const uint4 *>(base + (int64_t)w * cp);
+        const uint4 d = *reinterpret_cast<const uint4 *>(base + (int64_t)w * cp + cp);
+        uint4 o;
+        const __half2 *pa = reinterpret_cast<const __half2 *>(&a), *pb = reinterpret_cast<const __half2 *>(&b);
+        const __half2 *pc = reinterpret_cast<const __half2 *>(&c), *pd = reinterpret_cast<const __half2 *>(&d);
+        __half2 *po = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) po[q] = __hmax2(__hmax2(pa[q], pb[q]), __hmax2(pc[q], pd[q]));
+        *reinterpret_cast<uint4 *>(out + ((img * ho + yo) * (int64_t)wo + xo) * cp + ch) = o;
+    }
+}
+
+// =============================================================================
+//  last layer: Conv2D 1x1 (C1 -> K) + sigmoid / softmax in fp32        unet.py:63
+//  The arithmetic is written with explicit round-to-nearest intrinsics so that the
+//  materialised (.predict) kernel and the fused ensemble kernel produce the same bits.
+// =============================================================================
+struct OutParams {                      // per model, in shared memory: w[K][c1p] then b[K]
+    const float *w;                     // device [K][c1p] fp32 (zero in the channel padding)
+    const float *b;                     // device [K]
+};
+
+template <int KMAX>
+__device__ __forceinline__ void pixel_probs(const __half *__restrict__ x /*c1p halves of one pixel*/, int c1p,
+                                            const float *__restrict__ w_s, const float *__restrict__ b_s, int K,
+                                            int act, float (&p)[KMAX]) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) p[k] = (k < K) ? b_s[k] : 0.f;
+    for (int c0 = 0; c0 < c1p; c0 += 8) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(x + c0);
+        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+        float xf[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(hv[q]); xf[2 * q] = f.x; xf[2 * q + 1] = f.y; }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                const float *wk = w_s + k * c1p + c0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) p[k] = __fmaf_rn(xf[j], wk[j], p[k]);
+            }
+        }
+    }
+    if (act == IMK_ACT_SIGMOID) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) p[k] = __fdiv_rn(1.0f, __fadd_rn(1.0f, __expf(-p[k])));
+    } else {
+        float mx = p[0];
+#pragma unroll
+        for (int k = 1; k < KMAX; ++k) if (k < K) mx = fmaxf(mx, p[k]);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) { p[k] = __expf(__fsub_rn(p[k], mx)); sum = __fadd_rn(sum, p[k]); }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) p[k] = __fdiv_rn(p[k], sum);
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+out_probs_kernel(const __half *__restrict__ c9, int c1p, const float *__restrict__ w, const float *__restrict__ b,
+                 int K, int act, float *__restrict__ probs, int64_t total_px) {
+    extern __shared__ float osm[];
+    float *w_s = osm, *b_s = osm + K * c1p;
+    for (int i = threadIdx.x; i < K * c1p; i += blockDim.x) w_s[i] = w[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) b_s[i] = b[i];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < total_px; px += stride) {
+        float p[KMAX];
+        pixel_probs<KMAX>(c9 + px * c1p, c1p, w_s, b_s, K, act, p);
+        float *dst = probs + px * K;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) dst[k] = p[k];
+    }
+}
+
+// =============================================================================
+//  fused ensemble epilogue: for every pixel, every model's last layer + activation +
+//  threshold / argmax + ensemble agreement + IM + blanking + per-image sizes.  Reads the
+//  M fp16 c9 maps and the uint8 image, writes only uint8 maps: no fp32 map touches HBM.
+//  256 pixels per CTA iteration; label / IM bytes are regrouped through shared memory so
+//  that all uint8 traffic is 128-bit.
+// =============================================================================
+struct EnsPtrs {
+    const __half *c9[IMK_MAX_MODELS];
+    const float *w[IMK_MAX_MODELS];
+    const float *b[IMK_MAX_MODELS];
+};
+
+template <int KMAX, bool kMulticlass>
+__global__ void __launch_bounds__(256)
+ensemble_im_kernel(EnsPtrs ens, int M, int c1p, int K, int act, float thr, int strict,
+                   int64_t total_px, int64_t HW, int64_t N, int64_t plane_stride,
+                   const uint8_t *__restrict__ img, int c, int block_in, int block_out,
+                   uint8_t *__restrict__ img_out, uint8_t *__restrict__ labels, uint8_t *__restrict__ im_out,
+                   int64_t *__restrict__ im_size, int64_t *__restrict__ pred_size,
+                   unsigned long long *__restrict__ presence) {
+    // labels: plane k of this launch starts at labels + k * plane_stride; pred_size plane k at pred_size + k * N
+    extern __shared__ float esm[];
+    const int per_model = K * c1p + K;
+    float *w_all = esm;
+    uint8_t *bytes_s = reinterpret_cast<uint8_t *>(esm + (size_t)M * per_model);   // [4][256]: label0..2 / label, im
+    for (int m = 0; m < M; ++m) {
+        for (int i = threadIdx.x; i < K * c1p; i += blockDim.x) w_all[m * per_model + i] = ens.w[m][i];
+        for (int i = threadIdx.x; i < K; i += blockDim.x) w_all[m * per_model + K * c1p + i] = ens.b[m][i];
+    }
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (total_px + 255) / 256;
+    constexpr int NL = kMulticlass ? 1 : 3;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p0 = tile * 256;
+        const int64_t px = p0 + tid;
+        const bool live = px < total_px;
+        uint32_t im_any = 0, im_cnt = 0;
+        uint32_t lab[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) lab[l] = 0;
+        int a0 = 0;
+        uint32_t votes[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) votes[l] = 0;
+        const bool uniform = (p0 / HW) == ((p0 + 255) / HW) && (p0 + 256 <= total_px);
+        const int64_t n = live ? px / HW : -1;
+        const int64_t n_u = uniform ? p0 / HW : n;
+        for (int m = 0; m < M; ++m) {
+            int arg = 0;
+            if (live) {
+                float p[KMAX];
+                pixel_probs<KMAX>(ens.c9[m] + px * c1p, c1p, w_all + m * per_model, w_all + m * per_model + K * c1p, K, act, p);
+                if (kMulticlass) {
+                    float best = p[0];
+#pragma unroll
+                    for (int k = 1; k < KMAX; ++k) if (k < K) argmax_step(p[k], k, best, arg);
+                    if (m == 0) a0 = arg; else im_any |= (arg != a0);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) if (k < K) votes[k] += decide(p[k], thr, strict != 0);
+                }
+            }
+            if (kMulticlass && presence)
+                warp_or_stat(presence, n_u < 0 ? -1 : n_u * M + m, live ? (1ull << (arg & 63)) : 0ull, uniform);
+        }
+        if (kMulticlass) {
+            im_cnt = im_any;
+            lab[0] = im_any ? 0 : (uint32_t)a0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                if (k < K) {
+                    const uint32_t all = votes[k] == (uint32_t)M;
+                    const uint32_t mixed = (votes[k] != 0u) & (votes[k] != (uint32_t)M);
+                    lab[k] = all;
+                    im_any |= mixed;
+                    im_cnt += mixed;
+                }
+            }
+        }
+        if (!live) { im_cnt = 0; im_any = 0; }
+        warp_add_stat(im_size, n_u, im_cnt, uniform);
+        if (!kMulticlass && pred_size) {
+#pragma unroll
+            for (int k = 0; k < NL; ++k)
+                if (k < K) warp_add_stat(pred_size + (int64_t)k * N, n_u, live ? lab[k] : 0u, uniform);
+        }
+        if (kMulticlass) {
+            bytes_s[tid] = (uint8_t)lab[0];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NL; ++k)
+                if (k < K) bytes_s[k * 256 + tid] = (lab[k] && !(block_out && k < 2 && im_any)) ? 255 : 0;   // head 2 (HeLa position) stays raw
+        }
+        bytes_s[3 * 256 + tid] = im_any ? 255 : 0;
+        __syncthreads();
+        if (tid < 16) {
+            const int64_t vpx = p0 + 16 * tid;
+            if (vpx < total_px) {          // total_px % 16 == 0 on this path
+                const uint4 imv = *reinterpret_cast<const uint4 *>(bytes_s + 3 * 256 + 16 * tid);
+                const int nl = kMulticlass ? 1 : K;
+                for (int k = 0; k < nl; ++k)
+                    stg_stream(labels + (int64_t)k * plane_stride + vpx, *reinterpret_cast<const uint4 *>(bytes_s + k * 256 + 16 * tid));
+                stg_stream(im_out + vpx, imv);
+                if (img_out) {
+                    const uint32_t wv[4] = {imv.x, imv.y, imv.z, imv.w};
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) bits |= ((wv[i >> 2] >> (8 * (i & 3))) & 1u) << i;
+                    blank_image16_any(img, img_out, c, vpx, bits, block_in != 0);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void lists_equal_kernel2(const unsigned long long *__restrict__ presence, int M, int64_t N,
+                                    uint8_t *__restrict__ lists_equal) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    bool eq = true;
+    for (int m = 1; m < M; ++m) eq &= presence[n * M + m] == presence[n * M];
+    lists_equal[n] = eq ? 1 : 0;
+}
+
+// =============================================================================
+//  host side: plan, packing, workspace, trunk
+// =============================================================================
+static int grid_1d(int64_t items, int per_block = 256, int per_sm = 8) {
+    int64_t b = (items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <typename T>
+static int upload(std::vector<void *> &owned, const std::vector<T> &host, T **dev) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, host.size() * sizeof(T) + 16) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", host.size() * sizeof(T)); return IMK_ENOMEM; }
+    owned.push_back(p);
+    IMK_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = reinterpret_cast<T *>(p);
+    return IMK_OK;
+}
+
+struct PlanItem { bool is_conv; int ks, cin, cout; };
+
+// creation order of the parameterised layers, unet.py:49-63
+static std::vector<PlanItem> make_plan(const imk_unet_desc &d, const int f[5]) {
+    std::vector<PlanItem> p;
+    auto conv = [&](int ks, int ci, int co) { p.push_back({true, ks, ci, co}); };
+    auto bn = [&](int ch) { p.push_back({false, 0, ch, ch}); };
+    conv(1, d.in_channels, f[0]); bn(f[0]);                                   // input_block
+    int cin = f[0];
+    for (int l = 0; l < 4; ++l) { conv(d.ks, cin, f[l]); conv(1, f[l], f[l]); bn(f[l]); cin = f[l]; }   // encoder_block x4
+    conv(d.ks, cin, f[4]); conv(1, f[4], f[3]); bn(f[3]);                     // bottleneck_block
+    cin = f[3];
+    const int c1s[4] = {f[3], f[2], f[1], f[0]}, c2s[4] = {f[2], f[1], f[0], f[0]};
+    for (int l = 0; l < 4; ++l) {                                             // decoder_block x4
+        conv(1, cin, c1s[l]); bn(c1s[l]); conv(d.ks, c1s[l], c1s[l]); conv(1, c1s[l], c2s[l]); bn(c2s[l]);
+        cin = c2s[l];
+    }
+    conv(1, cin, d.num_outputmasks);                                          // 'out'
+    return p;
+}
+
+int unet_reserve(imk_unet *net, int64_t n) {
+    if (n <= net->cap_n) return IMK_OK;
+    if (net->ws) { cudaFree(net->ws); net->ws = nullptr; net->cap_n = 0; }
+    size_t total = 0;
+    size_t off[5][3];
+    for (int l = 0; l < 5; ++l) {
+        const int h = net->desc.height >> l, w = net->desc.width >> l;
+        const int chp = pad_ch(l < 4 ? net->widths[l] : net->widths[4]);
+        // level 4 buffer `b` holds the 256a-wide bottleneck map, `a` the 128a-wide ones
+        for (int j = 0; j < 3; ++j) {
+            size_t bytes = (size_t)n * h * w * chp * sizeof(__half);
+            bytes = (bytes + 255) / 256 * 256;
+            off[l][j] = total;
+            total += bytes;
+        }
+        net->lvl[l].h = h; net->lvl[l].w = w; net->lvl[l].ch_p = chp;
+    }
+    if (cudaMalloc(&net->ws, total) != cudaSuccess) { set_error("unet workspace: cudaMalloc(%zu) failed", total); return IMK_ENOMEM; }
+    net->ws_bytes = total;
+    for (int l = 0; l < 5; ++l) {
+        net->lvl[l].skip = reinterpret_cast<__half *>((char *)net->ws + off[l][0]);
+        net->lvl[l].a = reinterpret_cast<__half *>((char *)net->ws + off[l][1]);
+        net->lvl[l].b = reinterpret_cast<__half *>((char *)net->ws + off[l][2]);
+    }
+    net->cap_n = n;
+    return IMK_OK;
+}
+
+static int launch_conv(imk_unet *net, const ConvLayer &L, const __half *in, const __half *in_lo, __half *out,
+                       int64_t n, int h, int w, cudaStream_t stream) {
+    if (net->engine == 1 && conv_tc_supported(L)) return conv_tc_launch(L, in, in_lo, out, nullptr, n, h, w, stream);
+    const int tiles_x = (w + kDT - 1) / kDT, tiles_y = (h + kDT - 1) / kDT;
+    dim3 grid(tiles_x * tiles_y, L.cout_p / kDCo, (unsigned)n);
+    if (L.ks == 3)
+        conv_direct_kernel<3><<<grid, 128, 0, stream>>>(in, in_lo, L.w_direct, L.bias, L.has_bn ? L.bn_scale : nullptr,
+                                                        L.bn_shift, out, h, w, L.cin_p, L.cout_p, tiles_x);
+    else
+        conv_direct_kernel<1><<<grid, 128, 0, stream>>>(in, in_lo, L.w_direct, L.bias, L.has_bn ? L.bn_scale : nullptr,
+                                                        L.bn_shift, out, h, w, L.cin_p, L.cout_p, tiles_x);
+    IMK_LAUNCHED();
+    return IMK_OK;
+}
+
+int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaStream_t stream) {
+    int rc = unet_reserve(net, n);
+    if (rc) return rc;
+    const imk_unet_desc &d = net->desc;
+    const ConvLayer *L = net->conv.data();
+    Level *lv = net->lvl;
+    const int64_t px0 = n * d.height * d.width;
+    // input block -> lvl0.b
+    {
+        const ConvLayer &c0 = L[0];
+        const int grid = grid_1d(px0 * (c0.cout_p / 8));
+        if (in_dtype == IMK_IN_U8)
+            in_conv_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
+                                                               c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
+        else
+            in_conv_kernel<float><<<grid, 256, 0, stream>>>((const float *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
+                                                             c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
+        IMK_LAUNCHED();
+    }
+    int li = 1;
+    const __half *x = lv[0].b;
+    // encoder: conv3 -> a ; conv1+BN -> skip ; maxpool -> next level's b
+    for (int l = 0; l < 4; ++l) {
+        if ((rc = launch_conv(net, L[li++], x, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, L[li++], lv[l].a, nullptr, lv[l].skip, n, lv[l].h, lv[l].w, stream))) return rc;
+        const int64_t items = n * (lv[l].h / 2) * (lv[l].w / 2) * (lv[l].ch_p / 8);
+        __half *pooled = (l < 3) ? lv[l + 1].b : lv[4].a;
+        maxpool_kernel<<<grid_1d(items), 256, 0, stream>>>(lv[l].skip, pooled, n, lv[l].h, lv[l].w, lv[l].ch_p);
+        IMK_LAUNCHED();
+        x = pooled;
+    }
+    // bottleneck: conv3 (128a -> 256a) -> lvl4.b ; conv1+BN (256a -> 128a) -> lvl4.skip
+    if ((rc = launch_conv(net, L[li++], x, nullptr, lv[4].b, n, lv[4].h, lv[4].w, stream))) return rc;
+    if ((rc = launch_conv(net, L[li++], lv[4].b, nullptr, lv[4].skip, n, lv[4].h, lv[4].w, stream))) return rc;
+    x = lv[4].skip;
+    // decoder: (up(x) + skip) conv1+BN -> a ; conv3 -> b ; conv1+BN -> a
+    for (int l = 3; l >= 0; --l) {
+        if ((rc = launch_conv(net, L[li++], lv[l].skip, x, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, L[li++], lv[l].a, nullptr, lv[l].b, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, L[li++], lv[l].b, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        x = lv[l].a;
+    }
+    return IMK_OK;       // c9 == lv[0].a
+}
+
+template <typename F>
+static int dispatch_kmax(int K, F &&f) {
+    if (K <= 4) return f(std::integral_constant<int, 4>{});
+    if (K <= 16) return f(std::integral_constant<int, 16>{});
+    return f(std::integral_constant<int, 64>{});
+}
+
+static int launch_out_probs(imk_unet *net, int64_t n, float *probs, cudaStream_t stream) {
+    const imk_unet_desc &d = net->desc;
+    const ConvLayer &Lo = net->conv.back();
+    const int64_t px = n * d.height * d.width;
+    const int K = d.num_outputmasks, c1p = Lo.cin_p;
+    const size_t smem = (size_t)(K * c1p + K) * sizeof(float);
+    return dispatch_kmax(K, [&](auto kmax) -> int {
+        constexpr int KM = decltype(kmax)::value;
+        IMK_CUDA(cudaFuncSetAttribute(out_probs_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        out_probs_kernel<KM><<<grid_1d(px, 256, 4), 256, smem, stream>>>(net->lvl[0].a, c1p, Lo.w_f32, Lo.bias, K, d.act_out, probs, px);
+        IMK_LAUNCHED();
+        return IMK_OK;
+    });
+}
+
+}  // namespace imk
+
+using namespace imk;
+
+extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *weights_host,
+                               const int64_t *weight_sizes, int n_weights, imk_unet_t **out) {
+    IMK_REQUIRE(desc && weights_host && weight_sizes && out, "imk_unet_create: NULL argument");
+    const imk_unet_desc &d = *desc;
+    IMK_REQUIRE(d.height > 0 && d.width > 0 && d.height % 16 == 0 && d.width % 16 == 0,
+                "imk_unet_create: height/width must be positive multiples of 16 (4 poolings), got %dx%d", d.height, d.width);
+    IMK_REQUIRE(d.in_channels >= 1 && d.in_channels <= 4, "imk_unet_create: in_channels=%d outside 1..4", d.in_channels);
+    IMK_REQUIRE(d.num_outputmasks >= 1 && d.num_outputmasks <= 64, "imk_unet_create: num_outputmasks=%d outside 1..64", d.num_outputmasks);
+    IMK_REQUIRE(d.ks == 1 || d.ks == 3, "imk_unet_create: ks=%d (1 or 3)", d.ks);
+    IMK_REQUIRE(d.act_out == IMK_ACT_SIGMOID || d.act_out == IMK_ACT_SOFTMAX, "imk_unet_create: act_out=%d", d.act_out);
+    if (!imk_device_available()) { set_error("imk_unet_create: no CUDA device (there is no CPU fallback)"); return IMK_ECUDA; }
+    int f[5];
+    const int base[5] = {16, 32, 64, 128, 256};
+    for (int i = 0; i < 5; ++i) {
+        f[i] = (int)(base[i] * (double)d.alpha);      // int(k * alpha), unet.py:49-61
+        IMK_REQUIRE(f[i] >= 1, "imk_unet_create: alpha=%g gives an empty layer", (double)d.alpha);
+    }
+    IMK_REQUIRE(pad_ch(f[0]) <= 64, "imk_unet_create: alpha=%g too wide for the output kernels (int(16*alpha) <= 64)", (double)d.alpha);
+    const std::vector<PlanItem> plan = make_plan(d, f);
+    int expect = 0;
+    for (const PlanItem &it : plan) expect += it.is_conv ? 2 : 4;
+    IMK_REQUIRE(n_weights == expect, "imk_unet_create: expected %d weight arrays (Keras get_weights order), got %d", expect, n_weights);
+
+    imk_unet *net = new imk_unet();
+    net->desc = d;
+    for (int i = 0; i < 5; ++i) net->widths[i] = f[i];
+    int wi = 0, rc = IMK_OK;
+    auto fail = [&](int code) { imk_unet_destroy(net); return code; };
+    for (size_t pi = 0; pi < plan.size(); ++pi) {
+        const PlanItem &it = plan[pi];
+        if (it.is_conv) {
+            ConvLayer L;
+            L.ks = it.ks; L.cin = it.cin; L.cout = it.cout;
+            L.cin_p = pad_ch(it.cin); L.cout_p = pad_ch(it.cout);
+            const int64_t wsz = (int64_t)it.ks * it.ks * it.cin * it.cout;
+            if (weight_sizes[wi] != wsz || weight_sizes[wi + 1] != it.cout) {
+                set_error("imk_unet_create: weight %d: expected kernel %dx%dx%dx%d (+bias %d), got sizes %lld, %lld", wi, it.ks, it.ks,
+                          it.cin, it.cout, it.cout, (long long)weight_sizes[wi], (long long)weight_sizes[wi + 1]);
+                return fail(IMK_EINVAL);
+            }
+            const float *k = weights_host[wi], *b = weights_host[wi + 1];
+            wi += 2;
+            net->n_params += wsz + it.cout;
+            const bool first = (pi == 0), last = (pi + 1 == plan.size());
+            if (first) {
+                std::vector<float> wf(k, k + wsz);                              // [1][1][c][cout] == [c][cout]
+                if ((rc = upload(net->owned, wf, &L.w_f32))) return fail(rc);
+            } else if (last) {
+                std::vector<float> wf((size_t)it.cout * L.cin_p, 0.f);          // [K][c1p]
+                for (int ci = 0; ci < it.cin; ++ci)
+                    for (int co = 0; co < it.cout; ++co) wf[(size_t)co * L.cin_p + ci] = k[(size_t)ci * it.cout + co];
+                if ((rc = upload(net->owned, wf, &L.w_f32))) return fail(rc);
+            } else {
+                std::vector<__half> wh((size_t)it.ks * it.ks * L.cin_p * L.cout_p, __float2half(0.f));
+                for (int tap = 0; tap < it.ks * it.ks; ++tap)
+                    for (int ci = 0; ci < it.cin; ++ci)
+                        for (int co = 0; co < it.cout; ++co)
+                            wh[((size_t)tap * L.cin_p + ci) * L.cout_p + co] =
+                                __float2half_rn(k[((size_t)tap * it.cin + ci) * it.cout + co]);
+                if ((rc = upload(net->owned, wh, &L.w_direct))) return fail(rc);
+                if (conv_tc_supported(L) && (rc = conv_tc_pack(L, k, net->owned))) return fail(rc);
+            }
+            std::vector<float> bias(last ? it.cout : L.cout_p, 0.f);
+            for (int co = 0; co < it.cout; ++co) bias[co] = b[co];
+            if ((rc = upload(net->owned, bias, &L.bias))) return fail(rc);
+            net->conv.push_back(L);
+        } else {
+            ConvLayer &L = net->conv.back();
+            for (int j = 0; j < 4; ++j)
+                if (weight_sizes[wi + j] != it.cin) {
+                    set_error("imk_unet_create: weight %d: BatchNormalization vector of %d expected, got %lld", wi + j, it.cin,
+                              (long long)weight_sizes[wi + j]);
+                    return fail(IMK_EINVAL);
+                }
+            const float *g = weights_host[wi], *be = weights_host[wi + 1], *mu = weights_host[wi + 2], *var = weights_host[wi + 3];
+            wi += 4;
+            net->n_params += 4 * (int64_t)it.cin;
+            std::vector<float> sc(L.cout_p, 0.f), sh(L.cout_p, 0.f);
+            for (int ch = 0; ch < it.cin; ++ch) {
+                sc[ch] = g[ch] / sqrtf(var[ch] + kBnEps);
+                sh[ch] = be[ch] - mu[ch] * sc[ch];
+            }
+            if ((rc = upload(net->owned, sc, &L.bn_scale))) return fail(rc);
+            if ((rc = upload(net->owned, sh, &L.bn_shift))) return fail(rc);
+            L.has_bn = true;
+        }
+    }
+    *out = net;
+    return IMK_OK;
+}
+
+extern "C" void imk_unet_destroy(imk_unet_t *net) {
+    if (!net) return;
+    for (void *p : net->owned) cudaFree(p);
+    if (net->ws) cudaFree(net->ws);
+    if (net->stage_in) cudaFree(net->stage_in);
+    if (net->stage_probs) cudaFree(net->stage_probs);
+    delete net;
+}
+
+extern "C" int imk_unet_param_count(const imk_unet_t *net, int64_t *count) {
+    IMK_REQUIRE(net && count, "imk_unet_param_count: NULL argument");
+    *count = net->n_params;
+    return IMK_OK;
+}
+
+extern "C" int imk_unet_set_engine(imk_unet_t *net, int engine) {
+    IMK_REQUIRE(net && (engine == 0 || engine == 1), "imk_unet_set_engine: engine must be 0 (direct) or 1 (tcgen05)");
+    net->engine = engine;
+    return IMK_OK;
+}
+
+extern "C" int imk_unet_set_swap_rb(imk_unet_t *net, int swap_rb) {
+    IMK_REQUIRE(net, "imk_unet_set_swap_rb: NULL handle");
+    net->desc.swap_rb = swap_rb ? 1 : 0;
+    return IMK_OK;
+}
+
+extern "C" int imk_unet_forward(imk_unet_t *net, const void *images_dev, int in_dtype, int64_t N,
+                                float *probs_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    IMK_REQUIRE(net && images_dev && probs_dev, "imk_unet_forward: NULL argument");
+    IMK_REQUIRE(in_dtype == IMK_IN_U8 || in_dtype == IMK_IN_F32, "imk_unet_forward: in_dtype=%d", in_dtype);
+    IMK_REQUIRE(N >= 0, "imk_unet_forward: N=%lld", (long long)N);
+    const imk_unet_desc &d = net->desc;
+    const size_t in_px_bytes = (size_t)d.in_channels * (in_dtype == IMK_IN_U8 ? 1 : 4);
+    const int64_t HW = (int64_t)d.height * d.width;
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxChunk) {
+        const int64_t n = (N - n0 < kMaxChunk) ? N - n0 : kMaxChunk;
+        int rc = unet_trunk(net, (const char *)images_dev + n0 * HW * in_px_bytes, in_dtype, n, stream);
+        if (rc) return rc;
+        if ((rc = launch_out_probs(net, n, probs_dev + n0 * HW * d.num_outputmasks, stream))) return rc;
+    }
+    return IMK_OK;
+}
+
+extern "C" int imk_unet_predict_host(imk_unet_t *net, const void *images_host, int in_dtype, int64_t N, float *probs_host) {
+    IMK_REQUIRE(net && images_host && probs_host, "imk_unet_predict_host: NULL argument");
+    IMK_REQUIRE(in_dtype == IMK_IN_U8 || in_dtype == IMK_IN_F32, "imk_unet_predict_host: in_dtype=%d", in_dtype);
+    IMK_REQUIRE(N >= 0, "imk_unet_predict_host: N=%lld", (long long)N);
+    const imk_unet_desc &d = net->desc;
+    const int64_t HW = (int64_t)d.height * d.width;
+    const size_t in_img = (size_t)HW * d.in_channels * (in_dtype == IMK_IN_U8 ? 1 : 4);
+    const size_t out_img = (size_t)HW * d.num_outputmasks * sizeof(float);
+    const int64_t chunk = N < kMaxChunk ? (N > 0 ? N : 1) : kMaxChunk;
+    if (net->stage_in_bytes < in_img * chunk) {
+        if (net->stage_in) cudaFree(net->stage_in);
+        net->stage_in = nullptr; net->stage_in_bytes = 0;
+        if (cudaMalloc(&net->stage_in, in_img * chunk) != cudaSuccess) { set_error("predict: cudaMalloc failed"); return IMK_ENOMEM; }
+        net->stage_in_bytes = in_img * chunk;
+    }
+    if (net->stage_probs_bytes < out_img * chunk) {
+        if (net->stage_probs) cudaFree(net->stage_probs);
+        net->stage_probs = nullptr; net->stage_probs_bytes = 0;
+        if (cudaMalloc(&net->stage_probs, out_img * chunk) != cudaSuccess) { set_error("predict: cudaMalloc failed"); return IMK_ENOMEM; }
+        net->stage_probs_bytes = out_img * chunk;
+    }
+    for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+        const int64_t n = (N - n0 < chunk) ? N - n0 : chunk;
+        IMK_CUDA(cudaMemcpyAsync(net->stage_in, (const char *)images_host + n0 * in_img, in_img * n, cudaMemcpyHostToDevice, 0));
+        int rc = imk_unet_forward(net, net->stage_in, in_dtype, n, net->stage_probs, nullptr);
+        if (rc) return rc;
+        IMK_CUDA(cudaMemcpyAsync((char *)probs_host + n0 * out_img, net->stage_probs, out_img * n, cudaMemcpyDeviceToHost, 0));
+    }
+    IMK_CUDA(cudaStreamSynchronize(0));
+    return IMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+//  fused ensemble calls
+// ---------------------------------------------------------------------------------------
+namespace imk {
+static thread_local unsigned long long *g_presence2 = nullptr;
+static thread_local size_t g_presence2_cap = 0;
+
+static int check_ensemble(imk_unet_t *const *nets, int M, const char *who) {
+    IMK_REQUIRE(nets && M >= 1 && M <= IMK_MAX_MODELS, "%s: M=%d outside 1..%d", who, M, IMK_MAX_MODELS);
+    for (int m = 0; m < M; ++m) {
+        IMK_REQUIRE(nets[m], "%s: nets[%d] is NULL", who, m);
+        const imk_unet_desc &a = nets[0]->desc, &b = nets[m]->desc;
+        IMK_REQUIRE(a.height == b.height && a.width == b.width && a.in_channels == b.in_channels &&
+                        a.num_outputmasks == b.num_outputmasks && a.act_out == b.act_out,
+                    "%s: model %d has a different input / output signature than model 0", who, m);
+    }
+    return IMK_OK;
+}
+
+template <int KMAX, bool MC>
+static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float thr, int strict, int64_t total_px, int64_t HW,
+                      int64_t N, int64_t plane_stride, const uint8_t *img, int c, int block_in, int block_out, uint8_t *img_out, uint8_t *labels,
+                      uint8_t *im, int64_t *im_size, int64_t *pred_size, unsigned long long *presence, cudaStream_t stream) {
+    const size_t smem = (size_t)M * (K * c1p + K) * sizeof(float) + 4 * 256;
+    IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = grid_1d(total_px, 256, 4);
+    ensemble_im_kernel<KMAX, MC><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, total_px, HW, N, plane_stride, img, c,
+                                                               block_in, block_out, img_out, labels, im, im_size, pred_size, presence);
+    IMK_LAUNCHED();
+    return IMK_OK;
+}
+}  // namespace imk
+
+static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images_dev, int64_t N,
+                        float thr, int strict, int block_in, int block_out,
+                        uint8_t *img_out, uint8_t *labels, uint8_t *im, int64_t *im_size, int64_t *pred_size,
+                        uint8_t *lists_equal, cudaStream_t stream, const char *who) {
+    int rc = check_ensemble(nets, M, who);
+    if (rc) return rc;
+    IMK_REQUIRE(images_dev && labels && im && im_size, "%s: NULL images/labels/im/im_size", who);
+    IMK_REQUIRE(N >= 0, "%s: N=%lld", who, (long long)N);
+    const imk_unet_desc &d = nets[0]->desc;
+    const int K = d.num_outputmasks;
+    if (!multiclass) IMK_REQUIRE(K == 1 || K == 3, "%s: binary IM needs K = 1 (ISIC) or 3 (HeLa), model has %d", who, K);
+    IMK_REQUIRE(!lists_equal || K <= 64, "%s: lists_equal needs K <= 64", who);
+    const int c1p = nets[0]->conv.back().cin_p;
+    for (int m = 0; m < M; ++m)
+        IMK_REQUIRE(nets[m]->conv.back().cin_p == c1p, "%s: models with different int(16*alpha) padding cannot share the fused epilogue", who);
+    if (N == 0) return IMK_OK;
+    const int64_t HW = (int64_t)d.height * d.width;
+    IMK_CUDA(cudaMemsetAsync(im_size, 0, sizeof(int64_t) * N, stream));
+    if (pred_size && !multiclass) IMK_CUDA(cudaMemsetAsync(pred_size, 0, sizeof(int64_t) * N * K, stream));
+    unsigned long long *presence = nullptr;
+    if (multiclass && lists_equal) {
+        const size_t need = sizeof(unsigned long long) * (size_t)N * M;
+        if (need > g_presence2_cap) {
+            if (g_presence2) cudaFree(g_presence2);
+            g_presence2 = nullptr; g_presence2_cap = 0;
+            if (cudaMalloc(&g_presence2, need) != cudaSuccess) { set_error("%s: cudaMalloc(%zu) failed", who, need); return IMK_ENOMEM; }
+            g_presence2_cap = need;
+        }
+        presence = g_presence2;
+        IMK_CUDA(cudaMemsetAsync(presence, 0, need, stream));
+    }
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxChunk) {
+        const int64_t n = (N - n0 < kMaxChunk) ? N - n0 : kMaxChunk;
+        EnsPtrs ens{};
+        for (int m = 0; m < M; ++m) {
+            if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, n, stream))) return rc;
+            ens.c9[m] = nets[m]->lvl[0].a;
+            ens.w[m] = nets[m]->conv.back().w_f32;
+            ens.b[m] = nets[m]->conv.back().bias;
+        }
+        // chunk view: pixel arrays offset by n0*HW, per-image statistics by n0; label planes stay N*HW apart
+        const uint8_t *img_c = images_dev + n0 * HW * d.in_channels;
+        uint8_t *img_out_c = img_out ? img_out + n0 * HW * d.in_channels : nullptr;
+        uint8_t *im_c = im + n0 * HW;
+        int64_t *im_size_c = im_size + n0;
+        const int64_t total_px = n * HW;
+        if (multiclass) {
+            rc = dispatch_kmax(K, [&](auto kmax) -> int {
+                return launch_ens<decltype(kmax)::value, true>(ens, M, c1p, K, d.act_out, 0.f, 1, total_px, HW, N, N * HW, img_c, d.in_channels,
+                                                               block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
+                                                               nullptr, presence ? presence + n0 * M : nullptr, stream);
+            });
+        } else {
+            rc = launch_ens<4, false>(ens, M, c1p, K, d.act_out, thr, strict, total_px, HW, N, N * HW, img_c, d.in_channels, block_in, block_out,
+                                      img_out_c, labels + n0 * HW, im_c, im_size_c, pred_size ? pred_size + n0 : nullptr, nullptr, stream);
+        }
+        if (rc) return rc;
+    }
+    if (multiclass && lists_equal) {
+        lists_equal_kernel2<<<(int)((N + 255) / 256), 256, 0, stream>>>(presence, M, N, lists_equal);
+        IMK_LAUNCHED();
+    }
+    return IMK_OK;
+}
+
+extern "C" int imk_ensemble_im_binary(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+                                      float thr, int strict_gt, int block_in, int block_out,
+                                      uint8_t *img_out_dev, uint8_t *labels_dev, uint8_t *im_dev,
+                                      int64_t *im_size_dev, int64_t *pred_size_dev, void *stream) {
+    return ensemble_run(nets, M, false, images_dev, N, thr, strict_gt, block_in, block_out, img_out_dev, labels_dev, im_dev,
+                        im_size_dev, pred_size_dev, nullptr, (cudaStream_t)stream, "imk_ensemble_im_binary");
+}
+
+extern "C" int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+                                          int block_in, int block_out,
+                                          uint8_t *img_out_dev, uint8_t *label_dev, uint8_t *im_dev,
+                                          int64_t *im_size_dev, uint8_t *lists_equal_dev, void *stream) {
+    return ensemble_run(nets, M, true, images_dev, N, 0.f, 1, block_in, block_out, img_out_dev, label_dev, im_dev,
+                        im_size_dev, nullptr, lists_equal_dev, (cudaStream_t)stream, "imk_ensemble_im_multiclass");
+}

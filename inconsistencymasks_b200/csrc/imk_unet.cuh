@@ -1,0 +1,62 @@
+// Internal description of one packed U-Net (reference unet.py:46-67) on the device.
+#pragma once
+#include <vector>
+#include "imk_common.cuh"
+
+namespace imk {
+
+constexpr int kChanPad = 16;            // activations are fp16 NHWC with channels padded to 16
+inline int pad_ch(int c) { return (c + kChanPad - 1) / kChanPad * kChanPad; }
+
+// One Conv2D(+ReLU)(+BatchNormalization) of the plan, packed for the kernels.
+struct ConvLayer {
+    int ks = 1, cin = 0, cout = 0, cin_p = 0, cout_p = 0;
+    bool has_bn = false;
+    __half *w_direct = nullptr;   // [ks*ks][cin_p][cout_p] fp16  (direct convolution engine)
+    __half *w_umma = nullptr;     // tcgen05 operand-B image, see imk_conv_tc.cu
+    float *w_f32 = nullptr;       // [ks*ks][cin][cout] fp32 (first / last layer only)
+    float *bias = nullptr;        // [cout_p] fp32, zero in the padding
+    float *bn_scale = nullptr;    // [cout_p] gamma / sqrt(var + eps)   (0 in the padding)
+    float *bn_shift = nullptr;    // [cout_p] beta - mean * scale        (0 in the padding)
+};
+
+struct Level {                    // buffers of one resolution level, sized for `cap_n` images
+    __half *skip = nullptr, *a = nullptr, *b = nullptr;
+    int h = 0, w = 0, ch_p = 0;
+};
+
+}  // namespace imk
+
+struct imk_unet {
+    imk_unet_desc desc{};
+    int widths[5] = {0, 0, 0, 0, 0};           // int(16a), int(32a), int(64a), int(128a), int(256a)
+    std::vector<imk::ConvLayer> conv;           // 24 layers in creation order (unet.py:49-63)
+    int64_t n_params = 0;
+    int engine = 1;
+    std::vector<void *> owned;                  // device allocations freed at destroy
+    // workspace (grown on demand), for `cap_n` images
+    int64_t cap_n = 0;
+    imk::Level lvl[5];
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    void *stage_in = nullptr;                   // staging for *_host calls
+    size_t stage_in_bytes = 0;
+    float *stage_probs = nullptr;
+    size_t stage_probs_bytes = 0;
+};
+
+namespace imk {
+
+// Runs the 23 hidden layers for images [n0, n0+n) and leaves c9 (decoder level-0
+// output, fp16 [n,H,W,C1p]) in net->lvl[0].a.  `images` points at image n0.
+int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaStream_t stream);
+int unet_reserve(imk_unet *net, int64_t n);
+constexpr int64_t kMaxChunk = 64;       // images per trunk pass (bounds the workspace)
+
+// imk_conv_tc.cu: tcgen05 implicit-GEMM engine.  Returns IMK_OK when it handled the layer.
+bool conv_tc_supported(const ConvLayer &L);
+int conv_tc_pack(ConvLayer &L, const float *hwio, std::vector<void *> &owned);
+int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo /*upsample+add source or null*/,
+                   __half *out, __half *pool_out, int64_t n, int h, int w, cudaStream_t stream);
+
+}  // namespace imk
