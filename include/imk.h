@@ -59,6 +59,21 @@ int64_t     imk_launch_count(void);
 /* 1 when a CUDA device is usable from this process, else 0 (never throws). */
 int         imk_device_available(void);
 
+/* Per-kernel device timing for the roofline report (bench.py).  Between begin and end
+ * every kernel the calling thread launches through the library is bracketed by CUDA
+ * events on its own stream; end synchronises the device and returns one entry per
+ * (kernel name, tag) with the launch count and the summed device time.  `tag` is the
+ * index of the U-Net layer (0..23, creation order of unet.py) for convolution kernels,
+ * -1 otherwise.  n_out receives the number of distinct entries (may exceed cap). */
+typedef struct imk_profile_entry {
+    char    name[48];
+    int     tag;
+    int64_t launches;
+    double  total_ms;
+} imk_profile_entry;
+int imk_profile_begin(void);
+int imk_profile_end(imk_profile_entry *out, int cap, int *n_out);
+
 /* ------------------------------------------------------------------------- *
  *  Row a5 / a6 : pred_masks_to_im_binary  (functions.py:3104-3120)
  *                pred_masks_to_im_multiclass (functions.py:3123-3137)

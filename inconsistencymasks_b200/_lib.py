@@ -23,6 +23,10 @@ class UNetDesc(C.Structure):
                 ("act_out", C.c_int), ("swap_rb", C.c_int)]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("tag", C.c_int), ("launches", C.c_int64), ("total_ms", C.c_double)]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); mirrors include/imk.h one to one
@@ -31,6 +35,8 @@ SIGNATURES = {
     "imk_last_error": (C.c_char_p, []),
     "imk_launch_count": (_i64, []),
     "imk_device_available": (_i, []),
+    "imk_profile_begin": (_i, []),
+    "imk_profile_end": (_i, [C.POINTER(ProfileEntry), _i, C.POINTER(_i)]),
     "imk_masks_to_im_binary": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "imk_masks_to_im_multiclass": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "imk_im_binary": (_i, [_vp, _i, _i64, _i, _i, _i, _f, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -80,3 +86,17 @@ def device_available() -> bool:
 
 def launch_count() -> int:
     return int(lib.imk_launch_count())
+
+
+def profile_begin() -> None:
+    check(lib.imk_profile_begin())
+
+
+def profile_end():
+    """-> list of dicts {name, tag, launches, total_ms}: device time per kernel since profile_begin()."""
+    cap = 256
+    buf = (ProfileEntry * cap)()
+    n = C.c_int()
+    check(lib.imk_profile_end(buf, cap, C.byref(n)))
+    return [dict(name=buf[i].name.decode(), tag=int(buf[i].tag), launches=int(buf[i].launches),
+                 total_ms=float(buf[i].total_ms)) for i in range(min(cap, n.value))]

@@ -4,6 +4,8 @@
 // 2932-2980, 3020-3066) minus PNG I/O.
 #include <stdarg.h>
 #include <algorithm>
+#include <map>
+#include <vector>
 #include "imk_unet.cuh"
 
 namespace imk {
@@ -19,6 +21,31 @@ void set_error(const char *fmt, ...) {
 }
 int64_t &launch_counter() { return g_launches; }
 
+// ---- per-kernel profiler ------------------------------------------------------------
+struct ProfRec { const char *name; int tag; cudaEvent_t a, b; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> *g_prof = nullptr;
+static thread_local std::vector<cudaEvent_t> *g_prof_pool = nullptr;
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool) g_prof_pool = new std::vector<cudaEvent_t>();
+    if (!g_prof_pool->empty()) { cudaEvent_t e = g_prof_pool->back(); g_prof_pool->pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfileScope::ProfileScope(const char *name, int tag, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_prof_on) return;
+    ProfRec r{name, tag, prof_event(), prof_event()};
+    cudaEventRecord(r.a, s);
+    g_prof->push_back(r);
+    slot = (int)g_prof->size() - 1;
+}
+ProfileScope::~ProfileScope() {
+    if (slot >= 0) cudaEventRecord((*g_prof)[slot].b, stream);
+}
+
 }  // namespace imk
 
 using namespace imk;
@@ -31,6 +58,47 @@ extern "C" int imk_device_available(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n > 0 ? 1 : 0;
+}
+
+extern "C" int imk_profile_begin(void) {
+    if (!g_prof) g_prof = new std::vector<ProfRec>();
+    g_prof->clear();
+    g_prof_on = true;
+    return IMK_OK;
+}
+
+extern "C" int imk_profile_end(imk_profile_entry *out, int cap, int *n_out) {
+    IMK_REQUIRE(n_out && (out || cap == 0), "imk_profile_end: NULL argument");
+    g_prof_on = false;
+    *n_out = 0;
+    if (!g_prof) return IMK_OK;
+    IMK_CUDA(cudaDeviceSynchronize());
+    std::map<std::pair<std::string, int>, std::pair<int64_t, double>> acc;
+    for (ProfRec &r : *g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto &e = acc[{r.name, r.tag}];
+            e.first += 1;
+            e.second += ms;
+        } else {
+            cudaGetLastError();
+        }
+        g_prof_pool->push_back(r.a);
+        g_prof_pool->push_back(r.b);
+    }
+    g_prof->clear();
+    int n = 0;
+    for (auto &kv : acc) {
+        if (n < cap) {
+            snprintf(out[n].name, sizeof(out[n].name), "%s", kv.first.first.c_str());
+            out[n].tag = kv.first.second;
+            out[n].launches = kv.second.first;
+            out[n].total_ms = kv.second.second;
+        }
+        ++n;
+    }
+    *n_out = n;
+    return IMK_OK;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -35,6 +35,16 @@ int64_t &launch_counter();
         }                                                                           \
     } while (0)
 
+// Optional per-kernel timing (imk_profile_begin / imk_profile_end): when active, a pair of
+// CUDA events brackets the launch on ITS stream; nothing synchronises until the end call.
+struct ProfileScope {
+    int slot;
+    cudaStream_t stream;
+    ProfileScope(const char *name, int tag, cudaStream_t s);
+    ~ProfileScope();
+};
+#define IMK_PROFILE(name, tag, stream) imk::ProfileScope imk_prof_scope_((name), (tag), (stream))
+
 // Call right after a <<<>>> launch.
 #define IMK_LAUNCHED()                                                              \
     do {                                                                            \

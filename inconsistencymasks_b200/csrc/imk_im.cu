@@ -415,6 +415,7 @@ extern "C" int imk_im_binary(const float *const *probs_dev, int M, int64_t N, in
     const int64_t HW = (int64_t)H * W, total = N * HW;
     IMK_CUDA(cudaMemsetAsync(im_size_dev, 0, sizeof(int64_t) * N, stream));
     if (pred_size_dev) IMK_CUDA(cudaMemsetAsync(pred_size_dev, 0, sizeof(int64_t) * N * K, stream));
+    IMK_PROFILE(vec ? "im_binary_vec" : "im_binary_generic", -1, stream);
     if (vec) {
         const int grid = grid_for((total + kChunkPx - 1) / kChunkPx, kBinWarps, 8);
         if (K == 1)
@@ -482,6 +483,8 @@ extern "C" int imk_im_multiclass(const float *const *probs_dev, int M, int64_t N
         if (P > 1024) P = 1024;
         if (P < 128) P = ((size_t)2 * 128 * per_px + 2 * 128 + 64 <= 200 * 1024) ? 128 : 0;
     }
+    {
+    IMK_PROFILE((vec && P > 0) ? "im_multiclass_tma" : "im_multiclass_generic", -1, stream);
     if (vec && P > 0) {
         const size_t smem = (size_t)2 * M * P * K * sizeof(float) + 2 * (size_t)P + 2 * sizeof(uint64_t);
         IMK_CUDA(cudaFuncSetAttribute(im_multiclass_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -495,6 +498,7 @@ extern "C" int imk_im_multiclass(const float *const *probs_dev, int M, int64_t N
                                                                img_out_dev, label_dev, im_dev, im_size_dev, presence);
     }
     IMK_LAUNCHED();
+    }
     if (lists_equal_dev) {
         lists_equal_kernel<<<(int)((N + 255) / 256), 256, 0, stream>>>(presence, M, N, lists_equal_dev);
         IMK_LAUNCHED();

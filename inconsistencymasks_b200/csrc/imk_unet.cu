@@ -476,9 +476,14 @@ int unet_reserve(imk_unet *net, int64_t n) {
     return IMK_OK;
 }
 
-static int launch_conv(imk_unet *net, const ConvLayer &L, const __half *in, const __half *in_lo, __half *out,
+static int launch_conv(imk_unet *net, int layer, const __half *in, const __half *in_lo, __half *out,
                        int64_t n, int h, int w, cudaStream_t stream) {
-    if (net->engine == 1 && conv_tc_supported(L)) return conv_tc_launch(L, in, in_lo, out, nullptr, n, h, w, stream);
+    const ConvLayer &L = net->conv[layer];
+    if (net->engine == 1 && conv_tc_supported(L)) {
+        IMK_PROFILE(L.ks == 3 ? "conv_tc3" : "conv_tc1", layer, stream);
+        return conv_tc_launch(L, in, in_lo, out, nullptr, n, h, w, stream);
+    }
+    IMK_PROFILE(L.ks == 3 ? "conv_direct3" : "conv_direct1", layer, stream);
     const int tiles_x = (w + kDT - 1) / kDT, tiles_y = (h + kDT - 1) / kDT;
     dim3 grid(tiles_x * tiles_y, L.cout_p / kDCo, (unsigned)n);
     if (L.ks == 3)
@@ -502,6 +507,7 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
     {
         const ConvLayer &c0 = L[0];
         const int grid = grid_1d(px0 * (c0.cout_p / 8));
+        IMK_PROFILE("in_conv", 0, stream);
         if (in_dtype == IMK_IN_U8)
             in_conv_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
                                                                c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
@@ -514,23 +520,24 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
     const __half *x = lv[0].b;
     // encoder: conv3 -> a ; conv1+BN -> skip ; maxpool -> next level's b
     for (int l = 0; l < 4; ++l) {
-        if ((rc = launch_conv(net, L[li++], x, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
-        if ((rc = launch_conv(net, L[li++], lv[l].a, nullptr, lv[l].skip, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, li++, x, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, li++, lv[l].a, nullptr, lv[l].skip, n, lv[l].h, lv[l].w, stream))) return rc;
         const int64_t items = n * (lv[l].h / 2) * (lv[l].w / 2) * (lv[l].ch_p / 8);
         __half *pooled = (l < 3) ? lv[l + 1].b : lv[4].a;
+        IMK_PROFILE("maxpool", -1, stream);
         maxpool_kernel<<<grid_1d(items), 256, 0, stream>>>(lv[l].skip, pooled, n, lv[l].h, lv[l].w, lv[l].ch_p);
         IMK_LAUNCHED();
         x = pooled;
     }
     // bottleneck: conv3 (128a -> 256a) -> lvl4.b ; conv1+BN (256a -> 128a) -> lvl4.skip
-    if ((rc = launch_conv(net, L[li++], x, nullptr, lv[4].b, n, lv[4].h, lv[4].w, stream))) return rc;
-    if ((rc = launch_conv(net, L[li++], lv[4].b, nullptr, lv[4].skip, n, lv[4].h, lv[4].w, stream))) return rc;
+    if ((rc = launch_conv(net, li++, x, nullptr, lv[4].b, n, lv[4].h, lv[4].w, stream))) return rc;
+    if ((rc = launch_conv(net, li++, lv[4].b, nullptr, lv[4].skip, n, lv[4].h, lv[4].w, stream))) return rc;
     x = lv[4].skip;
     // decoder: (up(x) + skip) conv1+BN -> a ; conv3 -> b ; conv1+BN -> a
     for (int l = 3; l >= 0; --l) {
-        if ((rc = launch_conv(net, L[li++], lv[l].skip, x, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
-        if ((rc = launch_conv(net, L[li++], lv[l].a, nullptr, lv[l].b, n, lv[l].h, lv[l].w, stream))) return rc;
-        if ((rc = launch_conv(net, L[li++], lv[l].b, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, li++, lv[l].skip, x, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, li++, lv[l].a, nullptr, lv[l].b, n, lv[l].h, lv[l].w, stream))) return rc;
+        if ((rc = launch_conv(net, li++, lv[l].b, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
         x = lv[l].a;
     }
     return IMK_OK;       // c9 == lv[0].a
@@ -552,6 +559,7 @@ static int launch_out_probs(imk_unet *net, int64_t n, float *probs, cudaStream_t
     return dispatch_kmax(K, [&](auto kmax) -> int {
         constexpr int KM = decltype(kmax)::value;
         IMK_CUDA(cudaFuncSetAttribute(out_probs_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IMK_PROFILE("out_probs", 23, stream);
         out_probs_kernel<KM><<<grid_1d(px, 256, 4), 256, smem, stream>>>(net->lvl[0].a, c1p, Lo.w_f32, Lo.bias, K, d.act_out, probs, px);
         IMK_LAUNCHED();
         return IMK_OK;
@@ -756,6 +764,7 @@ static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float 
     const size_t smem = (size_t)M * (K * c1p + K) * sizeof(float) + 4 * 256;
     IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_1d(total_px, 256, 4);
+    IMK_PROFILE("ensemble_im", -1, stream);
     ensemble_im_kernel<KMAX, MC><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, total_px, HW, N, plane_stride, img, c,
                                                                block_in, block_out, img_out, labels, im, im_size, pred_size, presence);
     IMK_LAUNCHED();
