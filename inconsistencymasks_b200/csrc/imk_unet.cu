@@ -305,7 +305,7 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p, int K, int act, float thr, int s
     extern __shared__ float esm[];
     const int per_model = K * c1p + K;
     float *w_all = esm;
-    uint8_t *bytes_s = reinterpret_cast<uint8_t *>(esm + (size_t)M * per_model);   // [4][256]: label0..2 / label, im
+    uint8_t *bytes_s = reinterpret_cast<uint8_t *>(esm + ((size_t)M * per_model + 3) / 4 * 4);   // 16-byte aligned [4][256]: label planes, im
     for (int m = 0; m < M; ++m) {
         for (int i = threadIdx.x; i < K * c1p; i += blockDim.x) w_all[m * per_model + i] = ens.w[m][i];
         for (int i = threadIdx.x; i < K; i += blockDim.x) w_all[m * per_model + K * c1p + i] = ens.b[m][i];
@@ -761,7 +761,7 @@ template <int KMAX, bool MC>
 static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float thr, int strict, int64_t total_px, int64_t HW,
                       int64_t N, int64_t plane_stride, const uint8_t *img, int c, int block_in, int block_out, uint8_t *img_out, uint8_t *labels,
                       uint8_t *im, int64_t *im_size, int64_t *pred_size, unsigned long long *presence, cudaStream_t stream) {
-    const size_t smem = (size_t)M * (K * c1p + K) * sizeof(float) + 4 * 256;
+    const size_t smem = ((size_t)M * (K * c1p + K) + 3) / 4 * 4 * sizeof(float) + 4 * 256;
     IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_1d(total_px, 256, 4);
     IMK_PROFILE("ensemble_im", -1, stream);
