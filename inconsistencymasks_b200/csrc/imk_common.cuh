@@ -53,18 +53,12 @@ struct ProfileScope {
     } while (0)
 
 // ---- device helpers ----------------------------------------------------------
-// Streaming 128-bit accesses: every byte of the IM path is touched once, keep it
-// out of L1 (guide: ld.global.nc.L1::no_allocate / st.global.L1::no_allocate).
-__device__ __forceinline__ uint4 ldg_stream(const void *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void stg_stream(void *p, const uint4 &v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
+// Streaming 128-bit accesses: every byte of the IM path is touched once
+// (ld.global.cs / st.global.cs: streaming, evict-first; plain intrinsics so the compiler is
+// free to batch many independent loads per thread -- memory-level parallelism is what
+// saturates HBM here).
+__device__ __forceinline__ uint4 ldg_stream(const void *p) { return __ldcs(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ void stg_stream(void *p, const uint4 &v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }

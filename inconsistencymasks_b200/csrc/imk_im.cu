@@ -25,9 +25,20 @@ struct ProbPtrs {
 constexpr int kBinWarps = 8;     // 256 threads
 constexpr int kChunkPx = 512;    // pixels per warp iteration
 
-template <int K>
-__global__ void __launch_bounds__(kBinWarps * 32)
-im_binary_vec_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, float thr, int strict,
+// [px][3 heads] interleaved 0/1 bytes (12 words = 16 px) -> 3 head planes of 4 words each
+__device__ __forceinline__ void deinterleave3(const uint32_t (&w)[12], uint32_t (&plane)[3][4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+        plane[0][q] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);   // bytes 0, 3, 6, 9
+        plane[1][q] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);   // bytes 1, 4, 7, 10
+        plane[2][q] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);   // bytes 2, 5, 8, 11
+    }
+}
+
+template <int K, bool kStrict>
+__global__ void __launch_bounds__(kBinWarps * 32, 3)
+im_binary_vec_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, float thr,
                      const uint8_t *__restrict__ img, int c, int block_in, int block_out,
                      uint8_t *__restrict__ img_out, uint8_t *__restrict__ labels, uint8_t *__restrict__ im_out,
                      int64_t *__restrict__ im_size, int64_t *__restrict__ pred_size, int64_t N) {
@@ -36,91 +47,102 @@ im_binary_vec_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, float 
     const int warp = threadIdx.x >> 5;
     const int64_t n_chunks = (total_px + kChunkPx - 1) / kChunkPx;
     const int64_t warp_stride = (int64_t)gridDim.x * kBinWarps;
-    const bool strict_b = strict != 0;
+    const uint32_t m_rep = (uint32_t)M * 0x01010101u;
 
     for (int64_t chunk = (int64_t)blockIdx.x * kBinWarps + warp; chunk < n_chunks; chunk += warp_stride) {
         const int64_t px0 = chunk * kChunkPx;
+        const bool full = px0 + kChunkPx <= total_px;
         const int64_t rem_f = (total_px - px0) * K;           // floats left from the chunk start
         uint32_t cnt[4 * K];
 #pragma unroll
         for (int j = 0; j < 4 * K; ++j) cnt[j] = 0;
 
         for (int m = 0; m < M; ++m) {
-            const float *base = probs.p[m] + px0 * K;
+            const uint4 *base = reinterpret_cast<const uint4 *>(probs.p[m] + px0 * K) + lane;
             uint4 v[4 * K];
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 4 * K; ++j) {
-                const int f = (j * 32 + lane) * 4;
-                v[j] = (f < rem_f) ? ldg_stream(base + f) : make_uint4(0, 0, 0, 0);
+                for (int j = 0; j < 4 * K; ++j) v[j] = __ldcs(base + j * 32);       // 4K independent 128-bit loads in flight
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4 * K; ++j)
+                    v[j] = ((int64_t)(j * 32 + lane) * 4 < rem_f) ? __ldcs(base + j * 32) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int j = 0; j < 4 * K; ++j) {
-                cnt[j] += decide(__uint_as_float(v[j].x), thr, strict_b)
-                        | (decide(__uint_as_float(v[j].y), thr, strict_b) << 8)
-                        | (decide(__uint_as_float(v[j].z), thr, strict_b) << 16)
-                        | (decide(__uint_as_float(v[j].w), thr, strict_b) << 24);
+                cnt[j] += decide(__uint_as_float(v[j].x), thr, kStrict)
+                        | (decide(__uint_as_float(v[j].y), thr, kStrict) << 8)
+                        | (decide(__uint_as_float(v[j].z), thr, kStrict) << 16)
+                        | (decide(__uint_as_float(v[j].w), thr, kStrict) << 24);
             }
         }
         // transpose: element e (= px*K + head) of the chunk lives in byte e of the slab
 #pragma unroll
         for (int j = 0; j < 4 * K; ++j) slab[warp][j * 32 + lane] = cnt[j];
         __syncwarp();
-        uint32_t votes[4 * K];                                // K*16 bytes: [16 px][K heads]
+        uint32_t all01[4 * K], mix01[4 * K];                  // per element: every model fired / models disagree
 #pragma unroll
         for (int q = 0; q < K; ++q) {
             const uint4 t = *reinterpret_cast<const uint4 *>(&slab[warp][lane * 4 * K + 4 * q]);
-            votes[4 * q + 0] = t.x; votes[4 * q + 1] = t.y; votes[4 * q + 2] = t.z; votes[4 * q + 3] = t.w;
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t nz = bytes_nonzero01(w[e]);            // S != 0
+                const uint32_t ne = bytes_nonzero01(w[e] ^ m_rep);    // S != M
+                all01[4 * q + e] = ne ^ 0x01010101u;
+                mix01[4 * q + e] = nz & ne;
+            }
         }
         __syncwarp();
 
         const int64_t px = px0 + 16 * lane;
         const bool live = px < total_px;
-        uint32_t lab_bits[K];
-        uint32_t im_bits = 0, im_cnt = 0;
-        uint32_t pred_cnt[K];
+        uint32_t lab01[K][4], im01[4];
+        if constexpr (K == 1) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) { lab_bits[k] = 0; pred_cnt[k] = 0; }
+            for (int q = 0; q < 4; ++q) { lab01[0][q] = all01[q]; im01[q] = mix01[q]; }
+        } else {
+            uint32_t mixp[3][4];
+            deinterleave3(reinterpret_cast<const uint32_t (&)[12]>(all01), reinterpret_cast<uint32_t (&)[3][4]>(lab01));
+            deinterleave3(reinterpret_cast<const uint32_t (&)[12]>(mix01), mixp);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int e = i * K + k;
-                const uint32_t s = (votes[e >> 2] >> (8 * (e & 3))) & 0xFFu;
-                const uint32_t all = (s == (uint32_t)M);
-                const uint32_t mixed = (s != 0u) & (s != (uint32_t)M);
-                lab_bits[k] |= all << i;
-                im_bits |= mixed << i;
-                im_cnt += mixed;
-                pred_cnt[k] += all;
-            }
+            for (int q = 0; q < 4; ++q) im01[q] = mixp[0][q] | mixp[1][q] | mixp[2][q];    // combined IM = max over heads
         }
-        if (!live) { im_cnt = 0; }
-        // per-image statistics (counted before blanking, functions.py:3114-3115)
-        const bool uniform = (px0 / HW) == ((px0 + kChunkPx - 1) / HW) && (px0 + kChunkPx <= total_px);
-        const int64_t n = live ? px / HW : -1;
-        const int64_t n_u = uniform ? px0 / HW : n;
-        warp_add_stat(im_size, n_u, im_cnt, uniform);
+        // per-image statistics, counted before blanking (functions.py:3114-3115, 3200)
+        uint32_t im_cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4 * K; ++j) im_cnt += __popc(mix01[j]);
+        const int64_t n_lo = px0 / HW;
+        const bool uniform = full && (px0 + kChunkPx <= (n_lo + 1) * HW);
+        const int64_t n_u = uniform ? n_lo : (live ? px / HW : -1);
+        warp_add_stat(im_size, n_u, live ? im_cnt : 0u, uniform);
         if (pred_size) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) warp_add_stat(pred_size + (int64_t)k * N, n_u, live ? pred_cnt[k] : 0u, uniform);
+            for (int k = 0; k < K; ++k) {
+                uint32_t pc = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pc += __popc(lab01[k][q]);
+                warp_add_stat(pred_size + (int64_t)k * N, n_u, live ? pc : 0u, uniform);
+            }
         }
         if (live) {
-            auto expand = [](uint32_t bits16, int q) {       // 4 pixels -> 4 bytes of 0x00 / 0xFF
-                uint32_t w = 0;
+            uint32_t imw[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if ((bits16 >> (4 * q + e)) & 1u) w |= 0xFFu << (8 * e);
-                return w;
-            };
+            for (int q = 0; q < 4; ++q) imw[q] = bytes01_to_ff(im01[q]);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 // HeLa: the raw position head (k == 2) is never blanked -- the reference blanks the
                 // circle image drawn from it on the host instead (functions.py:2953-2974)
-                const uint32_t b = (block_out && k < 2) ? (lab_bits[k] & ~im_bits) : lab_bits[k];
-                stg_stream(labels + (int64_t)k * total_px + px,
-                           make_uint4(expand(b, 0), expand(b, 1), expand(b, 2), expand(b, 3)));
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    o[q] = bytes01_to_ff(lab01[k][q]);
+                    if (block_out && k < 2) o[q] &= ~imw[q];
+                }
+                stg_stream(labels + (int64_t)k * total_px + px, make_uint4(o[0], o[1], o[2], o[3]));
             }
-            stg_stream(im_out + px, make_uint4(expand(im_bits, 0), expand(im_bits, 1), expand(im_bits, 2), expand(im_bits, 3)));
-            if (img_out) blank_image16_any(img, img_out, c, px, im_bits, block_in != 0);
+            stg_stream(im_out + px, make_uint4(imw[0], imw[1], imw[2], imw[3]));
+            if (img_out) blank_image16_any(img, img_out, c, px, imw, block_in != 0);
         }
     }
 }
@@ -165,20 +187,30 @@ im_binary_generic_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
 }
 
 // =============================================================================
-//  multiclass, TMA path.  Persistent CTAs; each tile of P pixels of every model's
-//  [px][K] fp32 slab is brought into shared memory with one 1-D bulk copy
-//  (cp.async.bulk, SASS UBLKCP) per model, double-buffered on two mbarriers so the
-//  copy of tile i+1 overlaps the argmax of tile i.  One thread per pixel scans its K
-//  values from shared memory (pitch K words: conflict-free for odd K such as 9 / 35),
-//  label / IM bytes are regrouped through shared memory and leave as 128-bit stores.
+//  multiclass, TMA path.  Persistent CTAs of 8 consumer warps + 1 producer warp.
+//  The unit of transfer is ONE model's [P = 256 px][K] fp32 slab of a tile, brought into a
+//  ring of shared-memory slots with one 1-D bulk copy each (cp.async.bulk, SASS UBLKCP)
+//  signalled on a per-slot `full` mbarrier; consumers release a slot through its `empty`
+//  mbarrier (one arrive per warp), so several slabs (up to ~170 KB per SM) are always in
+//  flight while the argmax of earlier slabs runs.  One thread per pixel scans its K values
+//  from shared memory (pitch K words: conflict-free for odd K such as 9 / 35) and carries
+//  (argmax of model 0, disagreement) in registers across the models.  The uint8 epilogue is
+//  warp-local: a ballot gives the 32-pixel IM mask, lanes 0-1 store label / IM as 128-bit
+//  vectors, lanes 0..2c-1 blank the image, 16 bytes each.
 // =============================================================================
-constexpr int kMcThreads = 256;
+constexpr int kMcConsumers = 256;
+constexpr int kMcThreads = kMcConsumers + 32;
+constexpr int kMcTile = 256;              // pixels per tile (one per consumer thread)
+constexpr int kMcMaxSlots = 8;
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -196,106 +228,98 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 __global__ void __launch_bounds__(kMcThreads)
-im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, int K, int P,
+im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, int K, int n_slots,
                          const uint8_t *__restrict__ img, int c, int block_in, int block_out,
                          uint8_t *__restrict__ img_out, uint8_t *__restrict__ label_out, uint8_t *__restrict__ im_out,
                          int64_t *__restrict__ im_size, unsigned long long *__restrict__ presence) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    // layout: [2][M][P*K] float | label_s[P] | im_s[P] | full[2]
-    float *stage_base = reinterpret_cast<float *>(smem_raw);
-    const size_t stage_floats = (size_t)M * P * K;
-    uint8_t *label_s = smem_raw + 2 * stage_floats * sizeof(float);
-    uint8_t *im_s = label_s + P;
-    uint64_t *full = reinterpret_cast<uint64_t *>(im_s + P);
+    // layout: [n_slots][kMcTile*K] float | lab_s[8 warps][32] | full[n_slots] | empty[n_slots]
+    float *slots = reinterpret_cast<float *>(smem_raw);
+    const size_t slot_floats = (size_t)kMcTile * K;
+    uint8_t *lab_s = smem_raw + (size_t)n_slots * slot_floats * sizeof(float);
+    uint64_t *full = reinterpret_cast<uint64_t *>(lab_s + 8 * 32);
+    uint64_t *empty = full + kMcMaxSlots;
 
-    const int tid = threadIdx.x;
-    const int64_t n_tiles = (total_px + P - 1) / P;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (total_px + kMcTile - 1) / kMcTile;
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int s = 0; s < n_slots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMcConsumers / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int64_t tile, int stage) {
-        const int64_t p0 = tile * P;
-        const int64_t pc = min((int64_t)P, total_px - p0);
-        const uint32_t bytes = (uint32_t)(pc * K * sizeof(float));
-        mbar_expect_tx(&full[stage], bytes * M);
-        for (int m = 0; m < M; ++m)
-            bulk_g2s(stage_base + stage * stage_floats + (size_t)m * P * K, probs.p[m] + p0 * K, bytes, &full[stage]);
-    };
+    if (warp == kMcConsumers / 32) {
+        // ---------------- producer: one elected lane streams (tile, model) slabs ----------------
+        if (lane == 0) {
+            int64_t q = 0;                                       // running slab index of this CTA
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int64_t p0 = tile * kMcTile;
+                const int64_t pc = min((int64_t)kMcTile, total_px - p0);
+                const uint32_t bytes = (uint32_t)(pc * K * sizeof(float));
+                for (int m = 0; m < M; ++m, ++q) {
+                    const int slot = (int)(q % n_slots);
+                    if (q >= n_slots) mbar_wait(&empty[slot], (uint32_t)(((q / n_slots) - 1) & 1));
+                    mbar_expect_tx(&full[slot], bytes);
+                    bulk_g2s(slots + slot * slot_floats, probs.p[m] + p0 * K, bytes, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
 
-    int64_t tile = blockIdx.x;
-    if (tid == 0 && tile < n_tiles) issue(tile, 0);
-    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
-        const int stage = it & 1;
-        const uint32_t parity = (it >> 1) & 1;
-        const int64_t next = tile + gridDim.x;
-        if (tid == 0 && next < n_tiles) issue(next, stage ^ 1);   // stage^1 was drained before the last barrier
-        mbar_wait(&full[stage], parity);
-
-        const int64_t p0 = tile * P;
-        const int pc = (int)min((int64_t)P, total_px - p0);
-        const float *st = stage_base + stage * stage_floats;
-        const bool uniform = (p0 / HW) == ((p0 + pc - 1) / HW);
-        const int64_t n_tile = p0 / HW;
-        for (int pb = 0; pb < pc; pb += kMcThreads) {           // pc, kMcThreads multiples of 16/32: warps stay converged
-            const int p = pb + tid;
-            const bool live = p < pc;
-            uint32_t disagree = 0;
-            int a0 = 0;
+    // ---------------- consumers: thread p owns pixel p of the tile ----------------
+    int64_t q = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p0 = tile * kMcTile;
+        const int pc = (int)min((int64_t)kMcTile, total_px - p0);
+        const bool live = tid < pc;
+        const int64_t n_lo = p0 / HW;
+        const bool uniform = (p0 + pc <= (n_lo + 1) * HW);
+        const int64_t n_px = live ? (uniform ? n_lo : (p0 + tid) / HW) : -1;
+        uint32_t disagree = 0;
+        int a0 = 0;
+        for (int m = 0; m < M; ++m, ++q) {
+            const int slot = (int)(q % n_slots);
+            mbar_wait(&full[slot], (uint32_t)((q / n_slots) & 1));
+            int arg = 0;
             if (live) {
-                for (int m = 0; m < M; ++m) {
-                    const float *row = st + ((size_t)m * P + p) * K;
-                    float best = row[0];
-                    int arg = 0;
-                    for (int k = 1; k < K; ++k) argmax_step(row[k], k, best, arg);
-                    if (m == 0) a0 = arg; else disagree |= (arg != a0);
-                }
-                label_s[p] = disagree ? 0 : (uint8_t)a0;
-                im_s[p] = disagree ? 255 : 0;
+                arg = argmax_row(slots + slot * slot_floats + (size_t)tid * K, K);
+                if (m == 0) a0 = arg; else disagree |= (arg != a0);
             }
-            const int64_t n = live ? (p0 + p) / HW : -1;
-            warp_add_stat(im_size, uniform ? n_tile : n, live ? disagree : 0u, uniform);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);            // this warp is done with the slab
+            if (presence)
+                warp_or_stat(presence, n_px < 0 ? -1 : n_px * M + m, live ? (1ull << (arg & 63)) : 0ull, uniform && pc == kMcTile);
         }
-        if (presence) {
-            // class-set presence per (image, model): second pass keeps the hot loop lean
-            for (int m = 0; m < M; ++m) {
-                for (int pb = 0; pb < pc; pb += kMcThreads) {
-                    const int p = pb + tid;
-                    const bool live = p < pc;
-                    unsigned long long bit = 0;
-                    if (live) {
-                        const float *row = st + ((size_t)m * P + p) * K;
-                        float best = row[0];
-                        int arg = 0;
-                        for (int k = 1; k < K; ++k) argmax_step(row[k], k, best, arg);
-                        bit = 1ull << arg;
-                    }
-                    const int64_t n = live ? (p0 + p) / HW : -1;
-                    const int64_t nn = uniform ? n_tile : n;
-                    warp_or_stat(presence, nn < 0 ? -1 : nn * M + m, bit, uniform);
-                }
-            }
-        }
-        __syncthreads();
-        // 128-bit epilogue: 16 pixels per thread
-        for (int v = tid; v * 16 < pc; v += kMcThreads) {
-            const uint4 lab = *reinterpret_cast<const uint4 *>(label_s + 16 * v);
-            const uint4 imv = *reinterpret_cast<const uint4 *>(im_s + 16 * v);
-            const int64_t px = p0 + 16 * v;
-            stg_stream(label_out + px, lab);      // already 0 where the IM is set: block_out is a no-op here
-            stg_stream(im_out + px, imv);
-            if (img_out) {
-                const uint32_t w[4] = {imv.x, imv.y, imv.z, imv.w};
-                uint32_t bits = 0;
+        warp_add_stat(im_size, n_px, live ? disagree : 0u, uniform && pc == kMcTile);
+
+        // warp-local 128-bit epilogue over the warp's 32 consecutive pixels
+        const uint32_t im_mask = __ballot_sync(0xffffffffu, live && disagree);
+        lab_s[warp * 32 + lane] = (live && !disagree) ? (uint8_t)a0 : 0;
+        __syncwarp();
+        const int64_t wpx = p0 + warp * 32;                      // first pixel of this warp
+        if (lane < 2 && wpx + 16 * lane < p0 + pc) {
+            const int64_t px = wpx + 16 * lane;
+            const uint32_t bits = im_mask >> (16 * lane);
+            uint32_t imw[4];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) bits |= ((w[i >> 2] >> (8 * (i & 3))) & 1u) << i;
-                blank_image16_any(img, img_out, c, px, bits, block_in != 0);
+            for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(bits4_to_bytes01(bits >> (4 * j)));
+            stg_stream(label_out + px, *reinterpret_cast<const uint4 *>(lab_s + warp * 32 + 16 * lane));   // 0 where the IM is set
+            stg_stream(im_out + px, make_uint4(imw[0], imw[1], imw[2], imw[3]));
+        }
+        if (img_out && lane < 2 * c) {
+            const int g = lane / c, v = lane - g * c;            // 16-pixel group, 16-byte vector inside it
+            const int64_t px = wpx + 16 * g;
+            if (px < p0 + pc) {
+                const uint32_t bits = block_in ? (im_mask >> (16 * g)) : 0u;
+                uint32_t imw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(bits4_to_bytes01(bits >> (4 * j)));
+                const uint4 pix = ldg_stream(img + px * c + 16 * v);
+                stg_stream(img_out + px * c + 16 * v, blank_vec_rt(pix, imw, c, v));
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -315,9 +339,7 @@ im_multiclass_generic_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW
         for (int m = 0; m < M; ++m) {
             int arg = 0;
             if (live) {
-                const float *row = probs.p[m] + px * K;
-                float best = row[0];
-                for (int k = 1; k < K; ++k) argmax_step(row[k], k, best, arg);
+                arg = argmax_row(probs.p[m] + px * K, K);
                 if (m == 0) a0 = arg; else disagree |= (arg != a0);
             }
             if (presence) warp_or_stat(presence, n < 0 ? -1 : n * M + m, live ? (1ull << (arg & 63)) : 0ull, false);
@@ -417,15 +439,14 @@ extern "C" int imk_im_binary(const float *const *probs_dev, int M, int64_t N, in
     if (pred_size_dev) IMK_CUDA(cudaMemsetAsync(pred_size_dev, 0, sizeof(int64_t) * N * K, stream));
     IMK_PROFILE(vec ? "im_binary_vec" : "im_binary_generic", -1, stream);
     if (vec) {
-        const int grid = grid_for((total + kChunkPx - 1) / kChunkPx, kBinWarps, 8);
-        if (K == 1)
-            im_binary_vec_kernel<1><<<grid, kBinWarps * 32, 0, stream>>>(pp, M, total, HW, thr, strict_gt, img_dev, c, block_in,
-                                                                          block_out, img_out_dev, labels_dev, im_dev,
-                                                                          im_size_dev, pred_size_dev, N);
-        else
-            im_binary_vec_kernel<3><<<grid, kBinWarps * 32, 0, stream>>>(pp, M, total, HW, thr, strict_gt, img_dev, c, block_in,
-                                                                          block_out, img_out_dev, labels_dev, im_dev,
-                                                                          im_size_dev, pred_size_dev, N);
+        const int grid = grid_for((total + kChunkPx - 1) / kChunkPx, kBinWarps, 3);    // 3 resident CTAs per SM (register-bound)
+#define IMK_LAUNCH_BIN(KK, SS)                                                                                         \
+        im_binary_vec_kernel<KK, SS><<<grid, kBinWarps * 32, 0, stream>>>(pp, M, total, HW, thr, img_dev, c, block_in, block_out, \
+                                                                          img_out_dev, labels_dev, im_dev, im_size_dev,       \
+                                                                          pred_size_dev, N)
+        if (K == 1) { if (strict_gt) IMK_LAUNCH_BIN(1, true); else IMK_LAUNCH_BIN(1, false); }
+        else        { if (strict_gt) IMK_LAUNCH_BIN(3, true); else IMK_LAUNCH_BIN(3, false); }
+#undef IMK_LAUNCH_BIN
     } else {
         const int grid = grid_for(total, 256, 8);
         im_binary_generic_kernel<<<grid, 256, 0, stream>>>(pp, M, total, HW, K, thr, strict_gt, img_dev, c, block_in, block_out,
@@ -475,22 +496,23 @@ extern "C" int imk_im_multiclass(const float *const *probs_dev, int M, int64_t N
         presence = g_presence;
         IMK_CUDA(cudaMemsetAsync(presence, 0, need, stream));
     }
-    // tile size: the largest multiple of 128 pixels whose M slabs fit ~48 KB per stage
-    int P = 0;
-    if (vec) {
-        const size_t per_px = (size_t)M * K * sizeof(float);
-        P = (int)((48 * 1024) / per_px) / 128 * 128;
-        if (P > 1024) P = 1024;
-        if (P < 128) P = ((size_t)2 * 128 * per_px + 2 * 128 + 64 <= 200 * 1024) ? 128 : 0;
+    // ring depth / residency: prefer 3 CTAs per SM (24 consumer warps hide the shared-memory latency of
+    // the argmax scan) with at least a double buffer each; fall back to 2, then 1 CTA for wide K
+    const size_t slab_bytes = (size_t)kMcTile * K * sizeof(float);
+    int n_slots = 0, per_sm = 1;
+    for (int ctas = 3; ctas >= 1 && n_slots < 2; --ctas) {
+        per_sm = ctas;
+        n_slots = (int)(((size_t)216 * 1024 / ctas - 1024) / slab_bytes);
     }
+    if (n_slots > kMcMaxSlots) n_slots = kMcMaxSlots;
+    const bool tma = vec && n_slots >= 2;
     {
-    IMK_PROFILE((vec && P > 0) ? "im_multiclass_tma" : "im_multiclass_generic", -1, stream);
-    if (vec && P > 0) {
-        const size_t smem = (size_t)2 * M * P * K * sizeof(float) + 2 * (size_t)P + 2 * sizeof(uint64_t);
+    IMK_PROFILE(tma ? "im_multiclass_tma" : "im_multiclass_generic", -1, stream);
+    if (tma) {
+        const size_t smem = (size_t)n_slots * slab_bytes + 8 * 32 + 2 * kMcMaxSlots * sizeof(uint64_t);
         IMK_CUDA(cudaFuncSetAttribute(im_multiclass_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int per_sm = (int)((220 * 1024) / (smem + 1024));
-        const int grid = grid_for((total + P - 1) / P, 1, per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
-        im_multiclass_tma_kernel<<<grid, kMcThreads, smem, stream>>>(pp, M, total, HW, K, P, img_dev, c, block_in, block_out,
+        const int grid = grid_for((total + kMcTile - 1) / kMcTile, 1, per_sm);
+        im_multiclass_tma_kernel<<<grid, kMcThreads, smem, stream>>>(pp, M, total, HW, K, n_slots, img_dev, c, block_in, block_out,
                                                                      img_out_dev, label_dev, im_dev, im_size_dev, presence);
     } else {
         const int grid = grid_for(total, 256, 8);

@@ -387,11 +387,8 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p, int K, int act, float thr, int s
                     stg_stream(labels + (int64_t)k * plane_stride + vpx, *reinterpret_cast<const uint4 *>(bytes_s + k * 256 + 16 * tid));
                 stg_stream(im_out + vpx, imv);
                 if (img_out) {
-                    const uint32_t wv[4] = {imv.x, imv.y, imv.z, imv.w};
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) bits |= ((wv[i >> 2] >> (8 * (i & 3))) & 1u) << i;
-                    blank_image16_any(img, img_out, c, vpx, bits, block_in != 0);
+                    const uint32_t imw[4] = {imv.x, imv.y, imv.z, imv.w};
+                    blank_image16_any(img, img_out, c, vpx, imw, block_in != 0);
                 }
             }
         }
@@ -479,7 +476,7 @@ int unet_reserve(imk_unet *net, int64_t n) {
 static int launch_conv(imk_unet *net, int layer, const __half *in, const __half *in_lo, __half *out,
                        int64_t n, int h, int w, cudaStream_t stream) {
     const ConvLayer &L = net->conv[layer];
-    if (net->engine == 1 && conv_tc_supported(L)) {
+    if (net->engine == 1 && conv_tc_fits(L, h, w)) {
         IMK_PROFILE(L.ks == 3 ? "conv_tc3" : "conv_tc1", layer, stream);
         return conv_tc_launch(L, in, in_lo, out, nullptr, n, h, w, stream);
     }

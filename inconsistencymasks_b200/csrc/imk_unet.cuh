@@ -55,6 +55,7 @@ constexpr int64_t kMaxChunk = 64;       // images per trunk pass (bounds the wor
 
 // imk_conv_tc.cu: tcgen05 implicit-GEMM engine.  Returns IMK_OK when it handled the layer.
 bool conv_tc_supported(const ConvLayer &L);
+bool conv_tc_fits(const ConvLayer &L, int h, int w);   // a strip configuration exists for this resolution
 int conv_tc_pack(ConvLayer &L, const float *hwio, std::vector<void *> &owned);
 int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo /*upsample+add source or null*/,
                    __half *out, __half *pool_out, int64_t n, int h, int w, cudaStream_t stream);

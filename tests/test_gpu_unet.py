@@ -91,7 +91,9 @@ def test_engines_agree(U):
     a = model.predict(images)
     model.set_engine("tcgen05")
     b = model.predict(images)
-    assert np.abs(a - b).max() < 5e-3
+    d = np.abs(a - b)
+    print(f"\nengines: max|dp|={d.max():.3e} mean|dp|={d.mean():.3e}")
+    assert d.max() < PROB_ATOL and d.mean() < 5e-4
 
 
 def test_swap_rb(U):
