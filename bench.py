@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--im-images", type=int, default=1024)
     ap.add_argument("--cpu-images", type=int, default=256)
     ap.add_argument("--ref-images-per-step", type=int, default=32)
-    ap.add_argument("--engine", default=None, choices=[None, "direct", "tcgen05"])
+    ap.add_argument("--engine", default=None, choices=[None, "direct", "tcgen05", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -1,0 +1,55 @@
+// Descriptors of the block-fused tcgen05 engine (imk_block_tc.cu).
+#pragma once
+#include <vector>
+#include "imk_common.cuh"
+
+namespace imk {
+
+constexpr int kBtMaxBlocks = 24;        // M blocks (128 flat positions) per stage per tile
+
+struct BtStage {
+    int taps, ksteps, n, nb;            // 1|9, Cin_p/16, Cout_p (UMMA N), M blocks
+    int w_off;                          // byte offset of [tap][kstep][2][n][8] fp16 in the weight region
+    int par_off;                        // float offset of bias[n] | scale[n] | shift[n]
+    int col;                            // first TMEM column of the stage's accumulator region
+};
+
+struct BtArgs {
+    const void *in;                     // uint8 image (FRONT) or fp16 NHWC map
+    const __half *in_lo;                // DEC: the half-resolution map that is upsampled and added
+    __half *out;
+    const uint8_t *wpk;                 // packed weights of all stages (device)
+    const float *par;                   // bias / BN parameters of all stages (device)
+    int w_bytes, par_floats;
+    int H, W, in_c, swap_rb, load_kind, ld_cp;      // ld_cp: channels (padded) of the loaded operand
+    int in_f32;                         // FRONT: the image is float32 [N,H,W,c] instead of uint8
+    int Th, Tw, pitch, tiles_x, tiles_y;
+    long long n_tiles;
+    int has_s1;
+    BtStage s1, s2, s3;
+    int Pn0, Pn1, Pn2;
+    int par_off_b, a0_off, a1_off, a2_off, bar_off; // byte offsets in dynamic shared memory
+    unsigned pitch_magic;               // ceil(2^32 / pitch)
+};
+
+
+struct FusedBlock {                     // one fused U-Net block of one model (device-resident packs + plan)
+    bool ok = false;
+    BtArgs args{};
+    int w_bytes = 0, par_floats = 0;
+    size_t smem = 0;
+};
+
+struct ConvHost {                       // host view of one Conv2D (+BN) while imk_unet_create runs
+    const float *hwio, *bias;
+    const float *bn_scale, *bn_shift;   // folded BN (gamma / sqrt(var + eps), beta - mean * scale) or null
+    int ks, cin, cout;
+};
+
+// kind: 0 FRONT (in 1x1, conv3, conv1 of level 0), 1 ENC (conv3, conv1), 2 DEC (conv1a, conv3, conv1b).
+// Leaves fb.ok == false (and returns IMK_OK) when the block does not fit the resident-weight design.
+int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned);
+int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo, __half *out, int64_t n, int swap_rb,
+                       int in_f32, cudaStream_t stream);
+
+}  // namespace imk

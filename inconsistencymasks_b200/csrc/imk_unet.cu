@@ -476,7 +476,7 @@ int unet_reserve(imk_unet *net, int64_t n) {
 static int launch_conv(imk_unet *net, int layer, const __half *in, const __half *in_lo, __half *out,
                        int64_t n, int h, int w, cudaStream_t stream) {
     const ConvLayer &L = net->conv[layer];
-    if (net->engine == 1 && conv_tc_fits(L, h, w)) {
+    if (net->engine >= 1 && conv_tc_fits(L, h, w)) {
         IMK_PROFILE(L.ks == 3 ? "conv_tc3" : "conv_tc1", layer, stream);
         return conv_tc_launch(L, in, in_lo, out, nullptr, n, h, w, stream);
     }
@@ -500,41 +500,74 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
     const ConvLayer *L = net->conv.data();
     Level *lv = net->lvl;
     const int64_t px0 = n * d.height * d.width;
-    // input block -> lvl0.b
-    {
-        const ConvLayer &c0 = L[0];
-        const int grid = grid_1d(px0 * (c0.cout_p / 8));
-        IMK_PROFILE("in_conv", 0, stream);
-        if (in_dtype == IMK_IN_U8)
-            in_conv_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
-                                                               c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
-        else
-            in_conv_kernel<float><<<grid, 256, 0, stream>>>((const float *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
-                                                             c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
-        IMK_LAUNCHED();
-    }
-    int li = 1;
-    const __half *x = lv[0].b;
-    // encoder: conv3 -> a ; conv1+BN -> skip ; maxpool -> next level's b
-    for (int l = 0; l < 4; ++l) {
-        if ((rc = launch_conv(net, li++, x, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
-        if ((rc = launch_conv(net, li++, lv[l].a, nullptr, lv[l].skip, n, lv[l].h, lv[l].w, stream))) return rc;
+    const bool fused = net->engine == 2;
+    auto pool = [&](int l) -> const __half * {                     // MaxPooling2D of lvl[l].skip -> next level's input
         const int64_t items = n * (lv[l].h / 2) * (lv[l].w / 2) * (lv[l].ch_p / 8);
         __half *pooled = (l < 3) ? lv[l + 1].b : lv[4].a;
         IMK_PROFILE("maxpool", -1, stream);
         maxpool_kernel<<<grid_1d(items), 256, 0, stream>>>(lv[l].skip, pooled, n, lv[l].h, lv[l].w, lv[l].ch_p);
-        IMK_LAUNCHED();
-        x = pooled;
+        ++launch_counter();
+        return pooled;
+    };
+    int li = 1;
+    const __half *x = nullptr;
+    if (fused && net->fb_enc[0].ok) {
+        // input block + encoder block 1 in one kernel: image -> lvl0.skip
+        IMK_PROFILE("block_front", 0, stream);
+        if ((rc = fused_block_launch(net->fb_enc[0], images, nullptr, lv[0].skip, n, d.swap_rb, in_dtype == IMK_IN_F32, stream))) return rc;
+        li = 3;
+    } else {
+        {
+            const ConvLayer &c0 = L[0];
+            const int grid = grid_1d(px0 * (c0.cout_p / 8));
+            IMK_PROFILE("in_conv", 0, stream);
+            if (in_dtype == IMK_IN_U8)
+                in_conv_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
+                                                                   c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
+            else
+                in_conv_kernel<float><<<grid, 256, 0, stream>>>((const float *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
+                                                                 c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
+            IMK_LAUNCHED();
+        }
+        if ((rc = launch_conv(net, li++, lv[0].b, nullptr, lv[0].a, n, lv[0].h, lv[0].w, stream))) return rc;
+        if ((rc = launch_conv(net, li++, lv[0].a, nullptr, lv[0].skip, n, lv[0].h, lv[0].w, stream))) return rc;
+    }
+    x = pool(0);
+    IMK_CUDA(cudaGetLastError());
+    // encoder blocks 2..4: conv3 -> a ; conv1+BN -> skip ; maxpool -> next level's b
+    for (int l = 1; l < 4; ++l) {
+        if (fused && net->fb_enc[l].ok) {
+            IMK_PROFILE("block_enc", li, stream);
+            if ((rc = fused_block_launch(net->fb_enc[l], x, nullptr, lv[l].skip, n, 0, 0, stream))) return rc;
+            li += 2;
+        } else {
+            if ((rc = launch_conv(net, li++, x, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+            if ((rc = launch_conv(net, li++, lv[l].a, nullptr, lv[l].skip, n, lv[l].h, lv[l].w, stream))) return rc;
+        }
+        x = pool(l);
+        IMK_CUDA(cudaGetLastError());
     }
     // bottleneck: conv3 (128a -> 256a) -> lvl4.b ; conv1+BN (256a -> 128a) -> lvl4.skip
-    if ((rc = launch_conv(net, li++, x, nullptr, lv[4].b, n, lv[4].h, lv[4].w, stream))) return rc;
-    if ((rc = launch_conv(net, li++, lv[4].b, nullptr, lv[4].skip, n, lv[4].h, lv[4].w, stream))) return rc;
+    if (fused && net->fb_enc[4].ok) {
+        IMK_PROFILE("block_enc", li, stream);
+        if ((rc = fused_block_launch(net->fb_enc[4], x, nullptr, lv[4].skip, n, 0, 0, stream))) return rc;
+        li += 2;
+    } else {
+        if ((rc = launch_conv(net, li++, x, nullptr, lv[4].b, n, lv[4].h, lv[4].w, stream))) return rc;
+        if ((rc = launch_conv(net, li++, lv[4].b, nullptr, lv[4].skip, n, lv[4].h, lv[4].w, stream))) return rc;
+    }
     x = lv[4].skip;
     // decoder: (up(x) + skip) conv1+BN -> a ; conv3 -> b ; conv1+BN -> a
     for (int l = 3; l >= 0; --l) {
-        if ((rc = launch_conv(net, li++, lv[l].skip, x, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
-        if ((rc = launch_conv(net, li++, lv[l].a, nullptr, lv[l].b, n, lv[l].h, lv[l].w, stream))) return rc;
-        if ((rc = launch_conv(net, li++, lv[l].b, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        if (fused && net->fb_dec[l].ok) {
+            IMK_PROFILE("block_dec", li, stream);
+            if ((rc = fused_block_launch(net->fb_dec[l], lv[l].skip, x, lv[l].a, n, 0, 0, stream))) return rc;
+            li += 3;
+        } else {
+            if ((rc = launch_conv(net, li++, lv[l].skip, x, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+            if ((rc = launch_conv(net, li++, lv[l].a, nullptr, lv[l].b, n, lv[l].h, lv[l].w, stream))) return rc;
+            if ((rc = launch_conv(net, li++, lv[l].b, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
+        }
         x = lv[l].a;
     }
     return IMK_OK;       // c9 == lv[0].a
@@ -595,6 +628,8 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
     for (int i = 0; i < 5; ++i) net->widths[i] = f[i];
     int wi = 0, rc = IMK_OK;
     auto fail = [&](int code) { imk_unet_destroy(net); return code; };
+    std::vector<ConvHost> host;                                   // per conv, for the block-fused packs
+    std::vector<std::vector<float>> host_bn;                      // keeps the folded BN vectors alive
     for (size_t pi = 0; pi < plan.size(); ++pi) {
         const PlanItem &it = plan[pi];
         if (it.is_conv) {
@@ -633,6 +668,7 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
             for (int co = 0; co < it.cout; ++co) bias[co] = b[co];
             if ((rc = upload(net->owned, bias, &L.bias))) return fail(rc);
             net->conv.push_back(L);
+            host.push_back(ConvHost{k, b, nullptr, nullptr, it.ks, it.cin, it.cout});
         } else {
             ConvLayer &L = net->conv.back();
             for (int j = 0; j < 4; ++j)
@@ -652,6 +688,19 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
             if ((rc = upload(net->owned, sc, &L.bn_scale))) return fail(rc);
             if ((rc = upload(net->owned, sh, &L.bn_shift))) return fail(rc);
             L.has_bn = true;
+            host_bn.push_back(sc); host_bn.push_back(sh);
+        }
+    }
+    {   // block-fused packs (imk_block_tc.cu); a block that does not fit keeps ok == false and runs layer-wise
+        size_t bi = 0;
+        for (size_t ci = 0; ci < host.size(); ++ci)
+            if (net->conv[ci].has_bn) { host[ci].bn_scale = host_bn[bi].data(); host[ci].bn_shift = host_bn[bi + 1].data(); bi += 2; }
+        if (d.ks == 3) {
+            if ((rc = fused_block_build(net->fb_enc[0], 0, &host[0], d.height, d.width, d.in_channels, net->owned))) return fail(rc);
+            for (int l = 1; l < 5; ++l)
+                if ((rc = fused_block_build(net->fb_enc[l], 1, &host[1 + 2 * l], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
+            for (int l = 0; l < 4; ++l)
+                if ((rc = fused_block_build(net->fb_dec[l], 2, &host[11 + 3 * (3 - l)], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
         }
     }
     *out = net;
@@ -674,7 +723,7 @@ extern "C" int imk_unet_param_count(const imk_unet_t *net, int64_t *count) {
 }
 
 extern "C" int imk_unet_set_engine(imk_unet_t *net, int engine) {
-    IMK_REQUIRE(net && (engine == 0 || engine == 1), "imk_unet_set_engine: engine must be 0 (direct) or 1 (tcgen05)");
+    IMK_REQUIRE(net && engine >= 0 && engine <= 2, "imk_unet_set_engine: engine must be 0 (direct), 1 (tcgen05 layer-wise) or 2 (tcgen05 block-fused)");
     net->engine = engine;
     return IMK_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 #include "imk_common.cuh"
+#include "imk_block_tc.cuh"
 
 namespace imk {
 
@@ -32,7 +33,9 @@ struct imk_unet {
     int widths[5] = {0, 0, 0, 0, 0};           // int(16a), int(32a), int(64a), int(128a), int(256a)
     std::vector<imk::ConvLayer> conv;           // 24 layers in creation order (unet.py:49-63)
     int64_t n_params = 0;
-    int engine = 1;
+    int engine = 2;                             // 0 direct, 1 layer-wise tcgen05, 2 block-fused tcgen05 (falls back per block)
+    imk::FusedBlock fb_enc[5];                  // [0] = FRONT (in + enc1), [1..3] = enc2..4, [4] = bottleneck (conv3 + conv1, no pool)
+    imk::FusedBlock fb_dec[4];                  // decoder block that OUTPUTS level l
     std::vector<void *> owned;                  // device allocations freed at destroy
     // workspace (grown on demand), for `cap_n` images
     int64_t cap_n = 0;

@@ -124,8 +124,9 @@ class B200UNet:
         np.savez(path, __config__=np.array(repr(sorted(self.config.items()))), **arrs)
 
     def set_engine(self, engine):
-        """'tcgen05' (default) or 'direct' -- which CUDA convolution engine the wide layers use."""
-        check(lib.imk_unet_set_engine(self.handle, {"direct": 0, "tcgen05": 1}[engine]))
+        """'fused' (default: block-fused tcgen05, layer-wise where a block does not fit), 'tcgen05' (layer-wise
+        implicit GEMM) or 'direct' (CUDA cores) -- which convolution engine runs the hidden layers."""
+        check(lib.imk_unet_set_engine(self.handle, {"direct": 0, "tcgen05": 1, "fused": 2}[engine]))
 
     def set_swap_rb(self, flag):
         check(lib.imk_unet_set_swap_rb(self.handle, int(bool(flag))))

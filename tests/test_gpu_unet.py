@@ -51,7 +51,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("engine", ["direct", "tcgen05"])
+@pytest.mark.parametrize("engine", ["direct", "tcgen05", "fused"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}x{c[1]}c{c[2]}K{c[3]}a{c[4]}")
 def test_predict_vs_fp32_oracle(U, case, engine):
     h, w, c, K, alpha, act = case
@@ -93,6 +93,11 @@ def test_engines_agree(U):
     b = model.predict(images)
     d = np.abs(a - b)
     print(f"\nengines: max|dp|={d.max():.3e} mean|dp|={d.mean():.3e}")
+    assert d.max() < PROB_ATOL and d.mean() < 5e-4
+    model.set_engine("fused")          # block-fused: same rounding points except the hi/lo-split first layer
+    c_ = model.predict(images)
+    d = np.abs(b - c_)
+    print(f"fused vs layer-wise: max|dp|={d.max():.3e} mean|dp|={d.mean():.3e}")
     assert d.max() < PROB_ATOL and d.mean() < 5e-4
 
 
