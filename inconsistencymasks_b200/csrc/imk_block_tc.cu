@@ -14,31 +14,46 @@
 // TMEM (three regions R1/R2/R3, one per stage); the weights of all stages stay resident in
 // shared memory for the life of the CTA.
 //
-// Roles (416 threads, 1 CTA / SM, grid = min(tiles, 148), tiles strided over CTAs):
-//   warps 0-7   epilogue: tcgen05.ld -> +bias, ReLU, BN -> fp16 -> next stage's smem operand / global
-//               (warp w owns TMEM lanes 32*(w%4).., M blocks b = w/4 (mod 2))
-//   warp  8     TMEM allocation + single-thread tcgen05.mma issue
-//   warps 9-12  loaders: global -> smem operand of the first stage (uint8 image with hi/lo fp16
-//               split, plain cp.async copy, or nearest-upsample-2x + add)
-// The stages of consecutive tiles are software-pipelined so that the epilogue warps (the
-// instruction-issue bottleneck) never wait for the tensor pipe:
+// Roles (800 threads, 1 CTA / SM, grid = min(tiles, 148), tiles strided over CTAs):
+//   warps 0-15  epilogue: tcgen05.ld -> +bias, ReLU, BN -> fp16 -> next stage's smem operand / global
+//               (warp w owns TMEM lanes 32*(w%4).., M blocks b = w/4 (mod 4))
+//   warp  16    TMEM allocation + tcgen05.mma issue (one elected thread, fully unrolled K steps: a small-N
+//               SS MMA retires every ~39 cycles -- the A operand read, 4 KB at 128 B/clk -- so the issue
+//               sequence must not cost more than that)
+//   warps 17-24 loaders.  ENC / DEC: the haloed tile is ONE TMA box per 8-channel plane
+//               ({8 ch, pitch, Th+2, 1} of the NHWC map lands exactly as a plane of the flat layout, zero
+//               filled outside the image); DEC additionally TMA-loads the half-resolution tile into a
+//               staging area and the loader warps add it in place (nearest-upsample-2x + add, unet.py:32-33).
+//               FRONT: uint8 pixels through a 256-entry x/255 table, split into fp16 hi + lo K slots.
+// The stages of consecutive tiles are software-pipelined so that the epilogue warps never wait for
+// the tensor pipe:
 //   epilogue iteration i :  E1(i)            E3(i-1)          E2(i)
-//   MMA      iteration i :  S2(i)  S1(i+1)                    S3(i, block by block behind E2)
+//   MMA      iteration i :  S2(i)  S1(i+1)                    S3(i)
 //   loader               :  tile i+1 as soon as S1(i) / S2(i) has consumed the buffer
-// All hand-offs are mbarriers (tcgen05.commit on the MMA side), every barrier completes exactly
-// once per tile so the wait parity is the tile parity.
+// All hand-offs are mbarriers (tcgen05.commit on the MMA side, complete_tx on the TMA side); every
+// barrier completes exactly once per tile so the wait parity is the tile parity.
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 #include "imk_unet.cuh"
 
 namespace imk {
 
-constexpr int kBtEpiWarps = 8;
-constexpr int kBtLoadWarps = 4;
+constexpr int kBtEpiWarps = 16;
+constexpr int kBtEpiGroups = kBtEpiWarps / 4;
+constexpr int kBtLoadWarps = 8;
 constexpr int kBtThreads = (kBtEpiWarps + 1 + kBtLoadWarps) * 32;
 constexpr int kBtSmemMax = 227 * 1024;
+constexpr int kBtNumBars = 6 + 3 * kBtMaxBlocks;
 
 namespace {
+
+// timeline probe: role 0 = epilogue warp 0, 1 = MMA warp, 2 = loader warp 0 (CTA 0, first 16 tiles)
+#define BT_TL(role, i, ev)                                                                         \
+    do {                                                                                           \
+        if (a.dbg && blockIdx.x == 0 && (i) < 16 && (threadIdx.x & 31) == 0)                       \
+            a.dbg[((role) * 16 + (int)(i)) * 8 + (ev)] = clock64();                                \
+    } while (0)
 
 // ---- PTX wrappers ----------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -46,6 +61,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -77,68 +95,80 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major, no swizzle, version 1 (see imk_conv_tc.cu)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+__device__ __forceinline__ bool elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(e));
+    return e != 0;
+}
+// one TMA box {8 ch, box_w, box_h, 1} at (c, x, y, n) of a 4-D NHWC map -> dst (128-byte aligned shared memory)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c, int x, int y, int n, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(n), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tile_coords(const BtArgs &a, long long tile, long long &n, int &y0, int &x0) {
+__device__ __forceinline__ void tile_coords(const BtArgs &a, long long tile, int &n, int &y0, int &x0) {
     const int per_img = a.tiles_x * a.tiles_y;
-    n = tile / per_img;
-    const int r = (int)(tile - n * per_img);
+    n = (int)(tile / per_img);
+    const int r = (int)(tile - (long long)n * per_img);
     const int ty = r / a.tiles_x;
     y0 = ty * a.Th;
     x0 = (r - ty * a.tiles_x) * a.Tw;
 }
 
-// bias + ReLU + BN of 16 accumulator columns -> 8 packed half2 words
-__device__ __forceinline__ void epi16(const uint32_t (&r)[16], const float *__restrict__ p /*bias[n]|scale[n]|shift[n] at chunk*/,
-                                      int n, bool keep, uint4 &lo, uint4 &hi) {
+// bias + ReLU + BN of 16 accumulator columns -> 8 packed half2 words; p = bias[n] | scale[n] | shift[n] at the chunk
+__device__ __forceinline__ void epi16(const uint32_t (&r)[16], const float *__restrict__ p, int n, bool keep, uint4 &lo, uint4 &hi) {
     uint32_t o[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 b = *reinterpret_cast<const float4 *>(p + 4 * q);
         const float4 s = *reinterpret_cast<const float4 *>(p + n + 4 * q);
         const float4 t = *reinterpret_cast<const float4 *>(p + 2 * n + 4 * q);
-        float v0 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f), s.x, t.x);
-        float v1 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f), s.y, t.y);
-        float v2 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f), s.z, t.z);
-        float v3 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f), s.w, t.w);
-        if (!keep) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }
+        const float v0 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f), s.x, t.x);
+        const float v1 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f), s.y, t.y);
+        const float v2 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f), s.z, t.z);
+        const float v3 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f), s.w, t.w);
         const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
-        o[2 * q] = *reinterpret_cast<const uint32_t *>(&h0);
-        o[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&h1);
+        o[2 * q] = keep ? *reinterpret_cast<const uint32_t *>(&h0) : 0u;
+        o[2 * q + 1] = keep ? *reinterpret_cast<const uint32_t *>(&h1) : 0u;
     }
     lo = make_uint4(o[0], o[1], o[2], o[3]);
     hi = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// fp16x8 += fp16x8 with an fp32 add and one rounding (unet.py:33 `add`)
+__device__ __forceinline__ uint4 add_h8(const uint4 &v, const uint4 &u) {
+    const __half2 *pa = reinterpret_cast<const __half2 *>(&v);
+    const __half2 *pb = reinterpret_cast<const __half2 *>(&u);
+    uint4 r4;
+    __half2 *ro = reinterpret_cast<__half2 *>(&r4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 fa = __half22float2(pa[e]), fb = __half22float2(pb[e]);
+        ro[e] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+    }
+    return r4;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kBtThreads, 1)
-block_tc_kernel(const BtArgs a) {
+block_tc_kernel(const __grid_constant__ BtArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     float *par = reinterpret_cast<float *>(smem + a.par_off_b);
     uint8_t *A0 = smem + a.a0_off, *A1 = smem + a.a1_off, *A2 = smem + a.a2_off;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.bar_off);
-    uint64_t *ld_full = bars, *ld_empty = bars + 1, *e1_done = bars + 2, *e3_done = bars + 3;
-    uint64_t *acc1_full = bars + 4, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
-    uint64_t *e2_done = acc3_full + kBtMaxBlocks;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(e2_done + kBtMaxBlocks);
+    uint64_t *ld_full = bars, *ld_empty = bars + 1, *e1_done = bars + 2, *e2_done = bars + 3, *e3_done = bars + 4, *tma_full = bars + 5;
+    uint64_t *acc1_full = bars + 6, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kBtNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_my = (a.n_tiles - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(ld_full, kBtLoadWarps); mbar_init(ld_empty, 1);
-        mbar_init(e1_done, kBtEpiWarps); mbar_init(e3_done, kBtEpiWarps);
-        for (int b = 0; b < kBtMaxBlocks; ++b) {
-            mbar_init(&acc1_full[b], 1); mbar_init(&acc2_full[b], 1); mbar_init(&acc3_full[b], 1);
-            mbar_init(&e2_done[b], 4);
-        }
+        mbar_init(ld_full, kBtLoadWarps); mbar_init(ld_empty, 1); mbar_init(tma_full, 1);
+        mbar_init(e1_done, kBtEpiWarps); mbar_init(e2_done, kBtEpiWarps); mbar_init(e3_done, kBtEpiWarps);
+        for (int b = 0; b < kBtMaxBlocks; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc2_full[b], 1); mbar_init(&acc3_full[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kBtEpiWarps) {
@@ -154,6 +184,15 @@ block_tc_kernel(const BtArgs a) {
         const int zn = (a.bar_off - a.a0_off) / 16;
         for (int i = tid; i < zn; i += kBtThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
+    if (a.load_kind == 0) {                           // x/255 as fp16 hi + lo (the same arithmetic the float path uses)
+        __syncthreads();                              // the table lives inside the region zeroed above
+        if (tid < 256) {
+            const float xf = __fdiv_rn((float)tid, 255.0f);
+            const __half h = __float2half_rn(xf);
+            const __half l = __float2half_rn(xf - __half2float(h));
+            reinterpret_cast<uint32_t *>(smem + a.lut_off)[tid] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+        }
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -167,12 +206,13 @@ block_tc_kernel(const BtArgs a) {
         const int q = warp & 3, g = warp >> 2;
         const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
         for (long long i = 0; i <= n_my; ++i) {
-            long long n = 0; int y0 = 0, x0 = 0;
+            int n = 0, y0 = 0, x0 = 0;
             // ---- E1(i): S1 accumulators -> ReLU + BN, zero outside the image -> A1 (haloed flat layout)
             if (a.has_s1 && i < n_my) {
                 tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
                 const uint32_t par_ = (uint32_t)(i & 1);
-                for (int b = g; b < a.s1.nb; b += 2) {
+                if (warp == 0) BT_TL(0, i, 0);
+                for (int b = g; b < a.s1.nb; b += kBtEpiGroups) {
                     mbar_wait(&acc1_full[b], par_);
                     __syncwarp();
                     tc_fence_after();
@@ -190,18 +230,24 @@ block_tc_kernel(const BtArgs a) {
                         *reinterpret_cast<uint4 *>(A1 + ((size_t)((c0 >> 3) + 1) * a.Pn1 + m) * 16) = hi;
                     }
                 }
+                // warps without a block of their own still pace themselves on the stage (a free-running warp would
+                // arrive on e1_done for FUTURE tiles and corrupt the phase counts)
+                mbar_wait(&acc1_full[a.s1.nb - 1], par_);
                 fence_async_smem();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(e1_done);
+                if (warp == 0) BT_TL(0, i, 1);
             }
             // ---- E3(i-1): S3 accumulators -> ReLU + BN -> global
             if (i >= 1) {
                 tile_coords(a, (long long)blockIdx.x + (i - 1) * gridDim.x, n, y0, x0);
                 const uint32_t par_ = (uint32_t)((i - 1) & 1);
-                __half *out_n = a.out + n * (long long)a.H * a.W * a.s3.n;
-                for (int b = g; b < a.s3.nb; b += 2) {
+                __half *out_n = a.out + (long long)n * a.H * a.W * a.s3.n;
+                if (warp == 0) BT_TL(0, i, 2);
+                for (int b = g; b < a.s3.nb; b += kBtEpiGroups) {
                     mbar_wait(&acc3_full[b], par_);
+                    if (warp == 0 && b == g) BT_TL(0, i, 3);
                     __syncwarp();
                     tc_fence_after();
                     const int m = b * 128 + q * 32 + lane;
@@ -221,15 +267,18 @@ block_tc_kernel(const BtArgs a) {
                         }
                     }
                 }
+                mbar_wait(&acc3_full[a.s3.nb - 1], par_);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(e3_done);
+                if (warp == 0) BT_TL(0, i, 4);
             }
             // ---- E2(i): S2 accumulators -> ReLU -> A2 (flat layout, every row written)
             if (i < n_my) {
                 const uint32_t par_ = (uint32_t)(i & 1);
-                for (int b = g; b < a.s2.nb; b += 2) {
+                for (int b = g; b < a.s2.nb; b += kBtEpiGroups) {
                     mbar_wait(&acc2_full[b], par_);
+                    if (warp == 0 && b == g) BT_TL(0, i, 5);
                     __syncwarp();
                     tc_fence_after();
                     const int m = b * 128 + q * 32 + lane;
@@ -242,21 +291,20 @@ block_tc_kernel(const BtArgs a) {
                         *reinterpret_cast<uint4 *>(A2 + ((size_t)(c0 >> 3) * a.Pn2 + m) * 16) = lo;
                         *reinterpret_cast<uint4 *>(A2 + ((size_t)((c0 >> 3) + 1) * a.Pn2 + m) * 16) = hi;
                     }
-                    fence_async_smem();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&e2_done[b]);
                 }
+                mbar_wait(&acc2_full[a.s2.nb - 1], par_);
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e2_done);
+                if (warp == 0) BT_TL(0, i, 6);
             }
         }
     } else if (warp == kBtEpiWarps) {
         // =====================================================================================
-        //  MMA issue (one thread)
+        //  MMA issue: all lanes wait on the barriers, the tcgen05 instructions of a phase are issued
+        //  from inside ONE elect.sync region
         // =====================================================================================
-        // Every lane runs the (warp-uniform) bookkeeping so that the descriptor arithmetic stays in the uniform
-        // datapath; only the tcgen05 instructions themselves are issued by one elected lane.
-        uint32_t elected;
-        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(elected));
         const uint32_t wbase = smem_u32(smem);
         const uint32_t pitch = (uint32_t)a.pitch;
         // descriptor words: lo = addr >> 4 | LBO >> 4 << 16 ; hi = SBO >> 4 | version 1 << 14
@@ -277,61 +325,107 @@ block_tc_kernel(const BtArgs a) {
         const StageRegs S2 = make_stage(a.s2, smem_u32(A1), a.Pn1);
         const StageRegs S3 = make_stage(a.s3, smem_u32(A2), a.Pn2);
         auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-            if (elected)
-                tc_mma_f16(d, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, acc);
+            tc_mma_f16(d, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, acc);
         };
-        auto commit = [&](uint64_t *bar) { if (elected) tc_commit(bar); };
-        // one M block of a 1x1 stage: ksteps MMAs
-        auto block_1x1 = [&](const StageRegs &r, uint32_t b) {
+        // one M block of a 1x1 stage.  KS > 0: compile-time K steps (fully unrolled); KS == 0: runtime loop.
+        auto block_1x1 = [&](auto ks_tag, const StageRegs &r, uint32_t b) {
+            constexpr int KS = decltype(ks_tag)::value;
             const uint32_t d = r.d + b * r.n;
             uint32_t al = r.a_lo + b * 128u, bl = r.b_lo;
-            for (uint32_t j = 0; j < r.ksteps; ++j, al += r.a_step, bl += r.b_unit) mma(d, al, bl, r.idesc, j);
-        };
-        // one M block of the 3x3 stage: 9 taps x ksteps MMAs, the taps are offsets dy * pitch + dx into the flat tile
-        auto block_3x3 = [&](const StageRegs &r, uint32_t b) {
-            const uint32_t d = r.d + b * r.n;
-            uint32_t bl = r.b_lo, acc = 0;
-            uint32_t arow = r.a_lo + b * 128u;
+            if constexpr (KS > 0) {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy, arow += pitch) {
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    uint32_t al = arow + (uint32_t)dx;
-                    for (uint32_t j = 0; j < r.ksteps; ++j, al += r.a_step, bl += r.b_unit) { mma(d, al, bl, r.idesc, acc); acc = 1; }
-                }
+                for (int j = 0; j < KS; ++j) mma(d, al + (uint32_t)j * r.a_step, bl + (uint32_t)j * r.b_unit, r.idesc, (uint32_t)j);
+            } else {
+                for (uint32_t j = 0; j < r.ksteps; ++j, al += r.a_step, bl += r.b_unit) mma(d, al, bl, r.idesc, j);
             }
+        };
+        // one M block of the 3x3 stage: 9 taps x K steps, the taps are offsets dy * pitch + dx into the flat tile
+        auto block_3x3 = [&](auto ks_tag, const StageRegs &r, uint32_t b) {
+            constexpr int KS = decltype(ks_tag)::value;
+            const uint32_t d = r.d + b * r.n;
+            const uint32_t arow0 = r.a_lo + b * 128u;
+            if constexpr (KS > 0) {
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const uint32_t arow = arow0 + (uint32_t)dy * pitch;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                        for (int j = 0; j < KS; ++j)
+                            mma(d, arow + (uint32_t)dx + (uint32_t)j * r.a_step, r.b_lo + (uint32_t)((dy * 3 + dx) * KS + j) * r.b_unit, r.idesc,
+                                (uint32_t)((dy | dx | j) != 0));
+                    }
+                }
+            } else {
+                uint32_t bl = r.b_lo, acc = 0, arow = arow0;
+                for (int dy = 0; dy < 3; ++dy, arow += pitch)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        uint32_t al = arow + (uint32_t)dx;
+                        for (uint32_t j = 0; j < r.ksteps; ++j, al += r.a_step, bl += r.b_unit) { mma(d, al, bl, r.idesc, acc); acc = 1; }
+                    }
+            }
+        };
+        auto with_ks = [&](uint32_t ksteps, auto &&f) {
+            switch (ksteps) {
+                case 1: f(std::integral_constant<int, 1>{}); break;
+                case 2: f(std::integral_constant<int, 2>{}); break;
+                case 3: f(std::integral_constant<int, 3>{}); break;
+                case 4: f(std::integral_constant<int, 4>{}); break;
+                default: f(std::integral_constant<int, 0>{}); break;
+            }
+        };
+        auto issue_s1 = [&]() {
+            if (elect_one()) {
+                with_ks(S1.ksteps, [&](auto ks) {
+                    for (uint32_t b = 0; b < S1.nb; ++b) { block_1x1(ks, S1, b); tc_commit(&acc1_full[b]); }
+                });
+                tc_commit(ld_empty);
+            }
+            __syncwarp();
         };
         if (a.has_s1 && n_my > 0) {
             mbar_wait(ld_full, 0);
             tc_fence_after();
-            for (uint32_t b = 0; b < S1.nb; ++b) { block_1x1(S1, b); commit(&acc1_full[b]); }
-            commit(ld_empty);
+            issue_s1();
         }
         for (long long i = 0; i < n_my; ++i) {
             const uint32_t par_ = (uint32_t)(i & 1);
             // S2(i): its operand is A1 -- written by E1(i) (chain of three) or by the loaders (chain of two).
-            // R2 is free: every e2_done[b] of tile i-1 was waited for below.
+            // R2 is free: e2_done(i-1) was waited for below.
+            BT_TL(1, i, 0);
             mbar_wait(a.has_s1 ? e1_done : ld_full, par_);
             tc_fence_after();
-            for (uint32_t b = 0; b < S2.nb; ++b) { block_3x3(S2, b); commit(&acc2_full[b]); }
-            if (!a.has_s1) commit(ld_empty);
+            BT_TL(1, i, 1);
+            if (elect_one()) {
+                with_ks(S2.ksteps, [&](auto ks) {
+                    for (uint32_t b = 0; b < S2.nb; ++b) { block_3x3(ks, S2, b); tc_commit(&acc2_full[b]); }
+                });
+                if (!a.has_s1) tc_commit(ld_empty);
+            }
+            __syncwarp();
+            BT_TL(1, i, 2);
             // S1(i+1): R1 is free (e1_done(i) above)
             if (a.has_s1 && i + 1 < n_my) {
                 mbar_wait(ld_full, (uint32_t)((i + 1) & 1));
                 tc_fence_after();
-                for (uint32_t b = 0; b < S1.nb; ++b) { block_1x1(S1, b); commit(&acc1_full[b]); }
-                commit(ld_empty);
+                BT_TL(1, i, 3);
+                issue_s1();
             }
-            // S3(i), block by block behind E2(i); R3 is free once E3(i-1) has drained it
+            BT_TL(1, i, 4);
+            // S3(i): A2 complete and R2 drained (e2_done(i)); R3 free once E3(i-1) has drained it
             if (i > 0) { mbar_wait(e3_done, (uint32_t)((i - 1) & 1)); }
-            for (uint32_t b = 0; b < S3.nb; ++b) {
-                mbar_wait(&e2_done[b], par_);
-                tc_fence_after();
-                block_1x1(S3, b);
-                commit(&acc3_full[b]);
+            BT_TL(1, i, 5);
+            mbar_wait(e2_done, par_);
+            tc_fence_after();
+            BT_TL(1, i, 6);
+            if (elect_one()) {
+                with_ks(S3.ksteps, [&](auto ks) {
+                    for (uint32_t b = 0; b < S3.nb; ++b) { block_1x1(ks, S3, b); tc_commit(&acc3_full[b]); }
+                });
             }
+            __syncwarp();
+            BT_TL(1, i, 7);
         }
-        __syncwarp();
     } else {
         // =====================================================================================
         //  loaders
@@ -342,92 +436,119 @@ block_tc_kernel(const BtArgs a) {
         const int Pn = a.has_s1 ? a.Pn0 : a.Pn1;
         const int npos = (a.Th + 2) * a.pitch;
         const int KC = a.ld_cp >> 3;
+        const bool first = warp == kBtEpiWarps + 1;
         for (long long i = 0; i < n_my; ++i) {
-            long long n; int y0, x0;
+            int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
+            if (first) BT_TL(2, i, 0);
             if (i > 0) mbar_wait(ld_empty, (uint32_t)((i - 1) & 1));
+            if (first) BT_TL(2, i, 1);
             if (a.load_kind == 0) {
-                // uint8 image -> x/255 split into fp16 hi + lo so that the first layer keeps ~22 bits of the
-                // input and of the weights: K slots [hi(c) | lo(c) | hi(c)] against [w_hi | w_hi | w_lo]
-                const uint8_t *img = reinterpret_cast<const uint8_t *>(a.in) + n * (long long)a.H * a.W * a.in_c;
-                const float *imgf = reinterpret_cast<const float *>(a.in) + n * (long long)a.H * a.W * a.in_c;
-                for (int f = lt; f < npos; f += NL) {
-                    const int r = (int)__umulhi((unsigned)f, a.pitch_magic), c = f - r * a.pitch;
-                    const int y = y0 - 1 + r, x = x0 - 1 + c;
-                    __align__(16) __half v[16];
+                // image -> x/255 split into fp16 hi + lo so that the first layer keeps ~22 bits of the input and
+                // of the weights: K slots [hi(c) | lo(c) | hi(c)] against [w_hi | w_hi | w_lo]
+                const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem + a.lut_off);
+                if (!a.in_f32 && (a.in_c == 1 || a.in_c == 3)) {
+                    const uint8_t *img = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.H * a.W * a.in_c;
+                    constexpr int PB = 6;                    // positions in flight per thread
+                    for (int f0 = lt; f0 < npos; f0 += PB * NL) {
+                        uint32_t px[PB][3];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = __float2half_rn(0.f);
-                    if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
-                        const long long px = ((long long)y * a.W + x) * a.in_c;
-                        for (int ch = 0; ch < a.in_c; ++ch) {
-                            const int src = (a.swap_rb && a.in_c == 3) ? 2 - ch : ch;
-                            const float xf = __fdiv_rn(a.in_f32 ? imgf[px + src] : (float)img[px + src], 255.0f);
-                            const __half h = __float2half_rn(xf);
-                            const __half l = __float2half_rn(xf - __half2float(h));
-                            v[ch] = h; v[a.in_c + ch] = l; v[2 * a.in_c + ch] = h;
-                        }
-                    }
-                    *reinterpret_cast<uint4 *>(buf + (size_t)f * 16) = reinterpret_cast<const uint4 *>(v)[0];
-                    *reinterpret_cast<uint4 *>(buf + ((size_t)Pn + f) * 16) = reinterpret_cast<const uint4 *>(v)[1];
-                }
-            } else if (a.load_kind == 1) {
-                // plain copy of the haloed tile: 16-byte cp.async with zero fill outside the image
-                const __half *in_n = reinterpret_cast<const __half *>(a.in) + n * (long long)a.H * a.W * a.ld_cp;
-                const uint32_t dst0 = smem_u32(buf);
-                const int items = npos * KC;
-                for (int it = lt; it < items; it += NL) {
-                    const int f = it / KC, kc = it - f * KC;
-                    const int r = (int)__umulhi((unsigned)f, a.pitch_magic), c = f - r * a.pitch;
-                    const int y = y0 - 1 + r, x = x0 - 1 + c;
-                    const bool inside = y >= 0 && y < a.H && x >= 0 && x < a.W;
-                    const __half *src = inside ? in_n + ((long long)y * a.W + x) * a.ld_cp + kc * 8 : in_n;
-                    const uint32_t dst = dst0 + (uint32_t)(kc * Pn + f) * 16u;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(inside ? 16 : 0) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            } else {
-                // nearest-upsample-2x(lo) + skip (unet.py:32-33): fp32 add, one rounding
-                const __half *in_n = reinterpret_cast<const __half *>(a.in) + n * (long long)a.H * a.W * a.ld_cp;
-                const __half *lo_n = a.in_lo + n * (long long)(a.H >> 1) * (a.W >> 1) * a.ld_cp;
-                const int items = npos * KC;
-                for (int i0 = lt; i0 < items; i0 += 4 * NL) {
-                    uint4 v[4], u[4];
-                    int dst[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int it = i0 + k * NL;
-                        v[k] = make_uint4(0, 0, 0, 0); u[k] = make_uint4(0, 0, 0, 0); dst[k] = -1;
-                        if (it < items) {
-                            const int f = it / KC, kc = it - f * KC;
+                        for (int k = 0; k < PB; ++k) {
+                            const int f = f0 + k * NL;
                             const int r = (int)__umulhi((unsigned)f, a.pitch_magic), c = f - r * a.pitch;
                             const int y = y0 - 1 + r, x = x0 - 1 + c;
-                            dst[k] = kc * Pn + f;
-                            if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
-                                v[k] = __ldg(reinterpret_cast<const uint4 *>(in_n + ((long long)y * a.W + x) * a.ld_cp + kc * 8));
-                                u[k] = __ldg(reinterpret_cast<const uint4 *>(lo_n + ((long long)(y >> 1) * (a.W >> 1) + (x >> 1)) * a.ld_cp + kc * 8));
+                            const bool in = f < npos && y >= 0 && y < a.H && x >= 0 && x < a.W;
+                            const uint8_t *p = img + ((long long)y * a.W + x) * a.in_c;
+                            if (a.in_c == 1) {
+                                px[k][0] = in ? (uint32_t)__ldg(p) : 256u; px[k][1] = 256u; px[k][2] = 256u;
+                            } else {
+                                const int s0 = a.swap_rb ? 2 : 0, s2 = a.swap_rb ? 0 : 2;
+                                px[k][0] = in ? (uint32_t)__ldg(p + s0) : 256u;
+                                px[k][1] = in ? (uint32_t)__ldg(p + 1) : 256u;
+                                px[k][2] = in ? (uint32_t)__ldg(p + s2) : 256u;
                             }
                         }
-                    }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (dst[k] < 0) continue;
-                        const __half2 *pa = reinterpret_cast<const __half2 *>(&v[k]);
-                        const __half2 *pb = reinterpret_cast<const __half2 *>(&u[k]);
-                        uint4 r4;
-                        __half2 *ro = reinterpret_cast<__half2 *>(&r4);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 fa = __half22float2(pa[e]), fb = __half22float2(pb[e]);
-                            ro[e] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+                        for (int k = 0; k < PB; ++k) {
+                            const int f = f0 + k * NL;
+                            if (f >= npos) continue;
+                            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+                            if (px[k][0] != 256u) {
+                                if (a.in_c == 1) {
+                                    const uint32_t e = lut[px[k][0]];            // hi | lo << 16
+                                    w0.x = e; w0.y = e & 0xFFFFu;                 // slots: hi, lo, hi
+                                } else {
+                                    const uint32_t e0 = lut[px[k][0]], e1 = lut[px[k][1]], e2 = lut[px[k][2]];
+                                    const uint32_t h0 = e0 & 0xFFFFu, h1 = e1 & 0xFFFFu, h2 = e2 & 0xFFFFu;
+                                    w0.x = h0 | (h1 << 16);                       // hi0 hi1
+                                    w0.y = h2 | (e0 & 0xFFFF0000u);               // hi2 lo0
+                                    w0.z = (e1 >> 16) | (e2 & 0xFFFF0000u);       // lo1 lo2
+                                    w0.w = h0 | (h1 << 16);                       // hi0 hi1
+                                    w1.x = h2;                                    // hi2
+                                }
+                            }
+                            *reinterpret_cast<uint4 *>(buf + (size_t)f * 16) = w0;
+                            *reinterpret_cast<uint4 *>(buf + ((size_t)Pn + f) * 16) = w1;
                         }
-                        *reinterpret_cast<uint4 *>(buf + (size_t)dst[k] * 16) = r4;
+                    }
+                } else {
+                    // generic path: float32 images (benchmark_hela, functions.py:1199) or 2 / 4 channels
+                    const uint8_t *img = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.H * a.W * a.in_c;
+                    const float *imgf = reinterpret_cast<const float *>(a.in) + (long long)n * a.H * a.W * a.in_c;
+                    for (int f = lt; f < npos; f += NL) {
+                        const int r = (int)__umulhi((unsigned)f, a.pitch_magic), c = f - r * a.pitch;
+                        const int y = y0 - 1 + r, x = x0 - 1 + c;
+                        __align__(16) __half v[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = __float2half_rn(0.f);
+                        if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                            const long long px = ((long long)y * a.W + x) * a.in_c;
+                            for (int ch = 0; ch < a.in_c; ++ch) {
+                                const int src = (a.swap_rb && a.in_c == 3) ? 2 - ch : ch;
+                                const float xf = __fdiv_rn(a.in_f32 ? imgf[px + src] : (float)img[px + src], 255.0f);
+                                const __half h = __float2half_rn(xf);
+                                const __half l = __float2half_rn(xf - __half2float(h));
+                                v[ch] = h; v[a.in_c + ch] = l; v[2 * a.in_c + ch] = h;
+                            }
+                        }
+                        *reinterpret_cast<uint4 *>(buf + (size_t)f * 16) = reinterpret_cast<const uint4 *>(v)[0];
+                        *reinterpret_cast<uint4 *>(buf + ((size_t)Pn + f) * 16) = reinterpret_cast<const uint4 *>(v)[1];
+                    }
+                }
+            } else {
+                // the haloed tile: one TMA box per 8-channel plane, zero filled outside the image
+                const int yl0 = (y0 - 1) >> 1, xl0 = (x0 - 1) >> 1;
+                if (first && elect_one()) {
+                    const uint32_t tile_bytes = (uint32_t)KC * 16u * (uint32_t)npos;
+                    const uint32_t lo_bytes = a.load_kind == 2 ? (uint32_t)KC * 16u * (uint32_t)(a.pl_box * a.rl_box) : 0u;
+                    mbar_expect_tx(tma_full, tile_bytes + lo_bytes);
+                    const uint32_t dst = smem_u32(buf);
+                    for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, tma_full);
+                    if (a.load_kind == 2) {
+                        const uint32_t dlo = smem_u32(smem + a.lo_off);
+                        for (int kc = 0; kc < KC; ++kc) tma_load_4d(dlo + (uint32_t)(kc * a.Pl) * 16u, &a.tm_lo, kc * 8, xl0, yl0, n, tma_full);
+                    }
+                }
+                __syncwarp();
+                mbar_wait(tma_full, (uint32_t)(i & 1));
+                if (a.load_kind == 2) {
+                    // nearest-upsample-2x(lo) + skip (unet.py:32-33), in place: fp32 add, one rounding
+                    const uint8_t *lo_s = smem + a.lo_off;
+                    const int items = npos * KC;
+                    for (int it = lt; it < items; it += NL) {
+                        const int kc = it / npos, f = it - kc * npos;
+                        const int r = (int)__umulhi((unsigned)f, a.pitch_magic), c = f - r * a.pitch;
+                        const int yl = ((y0 - 1 + r) >> 1) - yl0, xl = ((x0 - 1 + c) >> 1) - xl0;
+                        uint4 *p = reinterpret_cast<uint4 *>(buf + ((size_t)kc * Pn + f) * 16);
+                        const uint4 u = *reinterpret_cast<const uint4 *>(lo_s + ((size_t)kc * a.Pl + yl * a.pl_box + xl) * 16);
+                        *p = add_h8(*p, u);
                     }
                 }
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(ld_full);
+            if (first) BT_TL(2, i, 2);
         }
     }
     // ---- teardown ----------------------------------------------------------------------------
@@ -493,53 +614,106 @@ static bool bt_disabled() {
 
 // Chooses the tile and lays out shared memory / TMEM.  Returns false when the block does not fit
 // (weights too large to stay resident, or no tile satisfies the 512-column TMEM budget).
+static inline int round8(int v) { return (v + 7) / 8 * 8; }
+
+struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, pl_box, rl_box, Pl; size_t bytes; };
+
+// shared-memory / TMEM footprint of a candidate tile; plane strides are multiples of 8 positions so that every
+// plane starts 128-byte aligned (TMA destination)
+static bool bt_geom(const FusedBlock &fb, int th, int tw, BtGeom &g) {
+    const BtArgs &a = fb.args;
+    const int pitch = tw + 2;
+    const int n1 = a.has_s1 ? a.s1.n : 0, n2 = a.s2.n, n3 = a.s3.n;
+    g.nb1 = a.has_s1 ? ((th + 2) * pitch + 127) / 128 : 0;
+    g.nb2 = (th * pitch + 127) / 128;
+    if (g.nb1 > kBtMaxBlocks || g.nb2 > kBtMaxBlocks) return false;
+    if (g.nb1 * n1 + g.nb2 * n2 + g.nb2 * n3 > 512) return false;
+    g.pl_box = (tw + 1) / 2 + 2; g.rl_box = th / 2 + 2;
+    if (pitch > 256 || g.pl_box > 256) return false;                 // TMA box limits
+    g.Pn0 = round8(g.nb1 * 128);
+    g.Pn1 = round8(std::max(std::max(g.nb1 * 128, g.nb2 * 128 + 2 * pitch + 2), (th + 2) * pitch));
+    g.Pn2 = round8(g.nb2 * 128);
+    g.Pl = round8(g.pl_box * g.rl_box);
+    size_t off = (size_t)fb.w_bytes + (size_t)fb.par_floats * 4;
+    off = (off + 127) / 128 * 128;
+    if (a.has_s1) off += (size_t)g.Pn0 * (a.s1.ksteps * 2) * 16;
+    off += (size_t)g.Pn1 * (a.s2.ksteps * 2) * 16;
+    off += (size_t)g.Pn2 * (a.s3.ksteps * 2) * 16;
+    if (a.load_kind == 2) off += (size_t)g.Pl * (a.ld_cp / 8) * 16;
+    if (a.load_kind == 0) off += 1024;
+    off += (size_t)kBtNumBars * 8 + 16;
+    g.bytes = off;
+    return off <= (size_t)kBtSmemMax;
+}
+
+// Chooses the tile and lays out shared memory / TMEM.  Returns false when the block does not fit
+// (weights too large to stay resident, or no tile satisfies the 512-column TMEM budget).
 static bool bt_plan(FusedBlock &fb, int H, int W) {
     BtArgs &a = fb.args;
     a.H = H; a.W = W;
-    const int n1 = a.has_s1 ? a.s1.n : 0, n2 = a.s2.n, n3 = a.s3.n;
     double best = -1.0;
     int bTh = 0, bTw = 0;
     const int th_opts[] = {8, 6, 4, 2};
+    BtGeom g{};
     for (int th : th_opts) {
         for (int split = 1; split <= 16; split *= 2) {
-            int tw = (W + split - 1) / split;
+            const int tw = (W + split - 1) / split;
             if (tw < 8 && split > 1) break;
-            const int pitch = tw + 2;
-            const int nb1 = a.has_s1 ? ((th + 2) * pitch + 127) / 128 : 0, nb2 = (th * pitch + 127) / 128;
-            if (nb1 > kBtMaxBlocks || nb2 > kBtMaxBlocks) continue;
-            if (nb1 * n1 + nb2 * n2 + nb2 * n3 > 512) continue;
-            const int Pn0 = (nb1 * 128) | 1;
-            const int Pn1 = std::max(nb1 * 128, nb2 * 128 + 2 * pitch + 2) | 1;
-            const int Pn2 = (nb2 * 128) | 1;
-            const size_t bytes = (size_t)fb.w_bytes + (size_t)fb.par_floats * 4 + 256 +
-                                 (a.has_s1 ? (size_t)Pn0 * (a.s1.ksteps * 2) * 16 : 0) + (size_t)Pn1 * (a.s2.ksteps * 2) * 16 +
-                                 (size_t)Pn2 * (a.s3.ksteps * 2) * 16 + (4 + 4 * kBtMaxBlocks) * 8 + 64;
-            if (bytes > (size_t)kBtSmemMax) continue;
+            if (!bt_geom(fb, th, tw, g)) continue;
             const int th_eff = std::min(th, H), tw_eff = std::min(tw, W);
             // useful fraction of the haloed work, with a mild preference for larger tiles (fewer hand-offs)
-            const double eff = (double)(th_eff * tw_eff) / ((th + 2.0) * pitch) + 1e-3 * th * tw / (8.0 * 256.0);
+            const double eff = (double)(th_eff * tw_eff) / ((th + 2.0) * (tw + 2.0)) + 1e-3 * th * tw / (8.0 * 256.0);
             if (eff > best) { best = eff; bTh = th; bTw = tw; }
         }
     }
     if (best < 0) return false;
+    bt_geom(fb, bTh, bTw, g);
     a.Th = bTh; a.Tw = bTw; a.pitch = bTw + 2;
     a.pitch_magic = (unsigned)((0x100000000ull + a.pitch - 1) / a.pitch);
     a.tiles_x = (W + bTw - 1) / bTw; a.tiles_y = (H + bTh - 1) / bTh;
-    a.s1.nb = a.has_s1 ? ((bTh + 2) * a.pitch + 127) / 128 : 0;
-    a.s2.nb = a.s3.nb = (bTh * a.pitch + 127) / 128;
-    a.s1.col = 0; a.s2.col = a.s1.nb * n1; a.s3.col = a.s2.col + a.s2.nb * n2;
-    a.Pn0 = (a.s1.nb * 128) | 1;
-    a.Pn1 = std::max(a.s1.nb * 128, a.s2.nb * 128 + 2 * a.pitch + 2) | 1;
-    a.Pn2 = (a.s2.nb * 128) | 1;
+    a.s1.nb = g.nb1; a.s2.nb = a.s3.nb = g.nb2;
+    a.s1.col = 0; a.s2.col = g.nb1 * (a.has_s1 ? a.s1.n : 0); a.s3.col = a.s2.col + g.nb2 * a.s2.n;
+    a.Pn0 = g.Pn0; a.Pn1 = g.Pn1; a.Pn2 = g.Pn2;
+    a.pl_box = g.pl_box; a.rl_box = g.rl_box; a.Pl = g.Pl;
     size_t off = (size_t)fb.w_bytes;
     a.par_off_b = (int)off; off += (size_t)fb.par_floats * 4; off = (off + 127) / 128 * 128;
     a.a0_off = (int)off; if (a.has_s1) off += (size_t)a.Pn0 * (a.s1.ksteps * 2) * 16;
     a.a1_off = (int)off; off += (size_t)a.Pn1 * (a.s2.ksteps * 2) * 16;
     a.a2_off = (int)off; off += (size_t)a.Pn2 * (a.s3.ksteps * 2) * 16;
-    off = (off + 15) / 16 * 16;
-    a.bar_off = (int)off; off += (4 + 4 * kBtMaxBlocks) * 8 + 16;
+    a.lo_off = (int)off; if (a.load_kind == 2) off += (size_t)a.Pl * (a.ld_cp / 8) * 16;
+    a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
+    a.bar_off = (int)off; off += (size_t)kBtNumBars * 8 + 16;        // everything in [a0_off, bar_off) starts zeroed
     fb.smem = off;
     return off <= (size_t)kBtSmemMax;
+}
+
+// ---- TMA tensor maps (driver entry point fetched through the runtime: no -lcuda) ---------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// fp16 NHWC [n, h, w, c] with boxes {8 ch, box_w, box_h, 1}; out-of-bounds elements read as zero
+static int make_map(CUtensorMap *map, const void *base, int64_t n, int h, int w, int c, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return IMK_ECUDA; }
+    const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+    const cuuint32_t box[4] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%lld,%d,%d,%d] box %dx%d", (int)r, (long long)n, h, w, c, box_w, box_h); return IMK_ECUDA; }
+    return IMK_OK;
 }
 
 static int bt_upload(FusedBlock &fb, const std::vector<__half> &w, const std::vector<float> &par, std::vector<void *> &owned) {
@@ -559,6 +733,7 @@ static int bt_upload(FusedBlock &fb, const std::vector<__half> &w, const std::ve
 int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned) {
     fb = FusedBlock{};
     if (bt_disabled()) return IMK_OK;
+    if (const char *v = getenv("IMK_BT_KINDS"); v && v[0] && !((atoi(v) >> kind) & 1)) return IMK_OK;   // debug: bitmask of fused kinds
     BtArgs &a = fb.args;
     std::vector<__half> w;
     std::vector<float> par;
@@ -603,14 +778,42 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
     a.in = in; a.in_lo = in_lo; a.out = out; a.swap_rb = swap_rb; a.in_f32 = in_f32;
     a.n_tiles = (long long)n * a.tiles_x * a.tiles_y;
     if (a.n_tiles <= 0) return IMK_OK;
+    if (a.load_kind != 0) {
+        int rc = make_map(&a.tm_in, in, n, a.H, a.W, a.ld_cp, a.pitch, a.Th + 2);
+        if (rc) return rc;
+        if (a.load_kind == 2 && (rc = make_map(&a.tm_lo, in_lo, n, a.H / 2, a.W / 2, a.ld_cp, a.pl_box, a.rl_box))) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         IMK_CUDA(cudaFuncSetAttribute(block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmemMax));
         attr_set = true;
     }
     const int grid = (int)std::min<long long>(a.n_tiles, kNumSMs);
+    static long long *dbg_dev = nullptr;
+    const char *tl = getenv("IMK_BT_TIMELINE");
+    a.dbg = nullptr;
+    if (tl && tl[0] == '1') {
+        if (!dbg_dev) IMK_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 3 * 16 * 8));
+        IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 3 * 16 * 8, stream));
+        a.dbg = dbg_dev;
+    }
     block_tc_kernel<<<grid, kBtThreads, fb.smem, stream>>>(a);
     IMK_LAUNCHED();
+    if (a.dbg) {
+        long long h[3 * 16 * 8];
+        IMK_CUDA(cudaStreamSynchronize(stream));
+        IMK_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        long long t0 = 0;
+        for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+        fprintf(stderr, "[imk] timeline kind=%d %dx%d tile %dx%d (cycles since first event; rows: tile, cols: events)\n", a.load_kind, a.H, a.W, a.Th, a.Tw);
+        const char *names[3] = {"epi ", "mma ", "load"};
+        for (int r = 0; r < 3; ++r)
+            for (int i = 0; i < 8; ++i) {
+                fprintf(stderr, "[imk]   %s t%d:", names[r], i);
+                for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", h[(r * 16 + i) * 8 + e] ? h[(r * 16 + i) * 8 + e] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+    }
     return IMK_OK;
 }
 

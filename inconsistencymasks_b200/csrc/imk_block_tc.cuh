@@ -1,5 +1,6 @@
 // Descriptors of the block-fused tcgen05 engine (imk_block_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <vector>
 #include "imk_common.cuh"
 
@@ -30,6 +31,11 @@ struct BtArgs {
     int Pn0, Pn1, Pn2;
     int par_off_b, a0_off, a1_off, a2_off, bar_off; // byte offsets in dynamic shared memory
     unsigned pitch_magic;               // ceil(2^32 / pitch)
+    int lo_off, Pl, pl_box, rl_box;     // DEC: staging of the half-resolution tile ([kc][rl_box * pl_box (+pad)][8 ch])
+    int lut_off;                        // FRONT: 256-entry table of x/255 as fp16 hi | lo << 16
+    alignas(64) CUtensorMap tm_in;      // TMA maps (ENC / DEC): {8 ch, pitch, Th + 2, 1} boxes of the fp16 NHWC input ...
+    alignas(64) CUtensorMap tm_lo;      // ... and {8 ch, pl_box, rl_box, 1} boxes of the half-resolution map
+    long long *dbg;                     // optional timeline buffer (IMK_BT_TIMELINE=1): [3 roles][16 tiles][8 events] clocks of CTA 0
 };
 
 
