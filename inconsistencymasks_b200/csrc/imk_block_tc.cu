@@ -34,6 +34,7 @@
 // barrier completes exactly once per tile so the wait parity is the tile parity.
 #include <algorithm>
 #include <type_traits>
+#include <math.h>
 #include <stdlib.h>
 #include "imk_unet.cuh"
 
@@ -42,9 +43,9 @@ namespace imk {
 constexpr int kBtEpiWarps = 16;
 constexpr int kBtEpiGroups = kBtEpiWarps / 4;
 constexpr int kBtLoadWarps = 8;
-constexpr int kBtThreads = (kBtEpiWarps + 1 + kBtLoadWarps) * 32;
+constexpr int kBtThreads = (kBtEpiWarps + 1 + kBtLoadWarps + 1) * 32;    // + one store warp
 constexpr int kBtSmemMax = 227 * 1024;
-constexpr int kBtNumBars = 6 + 3 * kBtMaxBlocks;
+constexpr int kBtNumBars = 7 + 3 * kBtMaxBlocks;
 
 namespace {
 
@@ -115,37 +116,70 @@ __device__ __forceinline__ void tile_coords(const BtArgs &a, long long tile, int
     x0 = (r - ty * a.tiles_x) * a.Tw;
 }
 
-// bias + ReLU + BN of 16 accumulator columns -> 8 packed half2 words; p = bias[n] | scale[n] | shift[n] at the chunk
-__device__ __forceinline__ void epi16(const uint32_t (&r)[16], const float *__restrict__ p, int n, bool keep, uint4 &lo, uint4 &hi) {
+// epilogue of 16 accumulator columns -> 8 packed half2 words.  STAGE and CH are compile-time so that every constant
+// is a constant-bank operand of the FADD / FMNMX itself (BtArgs is __grid_constant__): no loads, no registers.
+template <int STAGE, int CH>
+__device__ __forceinline__ void epi16(const BtArgs &a, const uint32_t (&r)[16], bool keep, uint4 &lo, uint4 &hi) {
     uint32_t o[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 b = *reinterpret_cast<const float4 *>(p + 4 * q);
-        const float4 s = *reinterpret_cast<const float4 *>(p + n + 4 * q);
-        const float4 t = *reinterpret_cast<const float4 *>(p + 2 * n + 4 * q);
-        const float v0 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f), s.x, t.x);
-        const float v1 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f), s.y, t.y);
-        const float v2 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f), s.z, t.z);
-        const float v3 = __fmaf_rn(fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f), s.w, t.w);
-        const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
-        o[2 * q] = keep ? *reinterpret_cast<const uint32_t *>(&h0) : 0u;
-        o[2 * q + 1] = keep ? *reinterpret_cast<const uint32_t *>(&h1) : 0u;
+    for (int q = 0; q < 8; ++q) {
+        float v0 = __uint_as_float(r[2 * q]) + a.cpar[STAGE][0][16 * CH + 2 * q];
+        float v1 = __uint_as_float(r[2 * q + 1]) + a.cpar[STAGE][0][16 * CH + 2 * q + 1];
+        v0 = fminf(fmaxf(v0, a.cpar[STAGE][1][16 * CH + 2 * q]), a.cpar[STAGE][2][16 * CH + 2 * q]);
+        v1 = fminf(fmaxf(v1, a.cpar[STAGE][1][16 * CH + 2 * q + 1]), a.cpar[STAGE][2][16 * CH + 2 * q + 1]);
+        const __half2 h = __floats2half2_rn(v0, v1);
+        o[q] = keep ? *reinterpret_cast<const uint32_t *>(&h) : 0u;
     }
     lo = make_uint4(o[0], o[1], o[2], o[3]);
     hi = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-// fp16x8 += fp16x8 with an fp32 add and one rounding (unet.py:33 `add`)
+// one M block of an epilogue phase: NCH chunks of 16 columns, TMEM -> constants -> fp16 -> dst planes / pixel-major tile
+//   PLANES: dst is an operand buffer, chunk c lands at plane 2c / 2c+1 (stride plane_bytes); else dst is the pixel's
+//   row in the output tile and chunk c lands 32 bytes further
+template <int STAGE, int NCH, bool PLANES>
+__device__ __forceinline__ void epi_block(const BtArgs &a, uint32_t taddr, bool keep, bool store, uint8_t *dst, size_t plane_bytes) {
+    auto chunk = [&](auto ch_tag) {
+        constexpr int CH = decltype(ch_tag)::value;
+        uint32_t rr[16];
+        tc_ld16(taddr + 16 * CH, rr);
+        tc_wait_ld();
+        uint4 lo, hi;
+        epi16<STAGE, CH>(a, rr, keep, lo, hi);
+        if (store) {
+            if (PLANES) {
+                *reinterpret_cast<uint4 *>(dst + (size_t)(2 * CH) * plane_bytes) = lo;
+                *reinterpret_cast<uint4 *>(dst + (size_t)(2 * CH + 1) * plane_bytes) = hi;
+            } else {
+                reinterpret_cast<uint4 *>(dst + 32 * CH)[0] = lo;
+                reinterpret_cast<uint4 *>(dst + 32 * CH)[1] = hi;
+            }
+        }
+    };
+    chunk(std::integral_constant<int, 0>{});
+    if constexpr (NCH > 1) chunk(std::integral_constant<int, 1>{});
+    if constexpr (NCH > 2) chunk(std::integral_constant<int, 2>{});
+    if constexpr (NCH > 3) chunk(std::integral_constant<int, 3>{});
+}
+
+template <typename F>
+__device__ __forceinline__ void with_nch(int n, F &&f) {
+    switch (n >> 4) {
+        case 1: f(std::integral_constant<int, 1>{}); break;
+        case 2: f(std::integral_constant<int, 2>{}); break;
+        case 3: f(std::integral_constant<int, 3>{}); break;
+        default: f(std::integral_constant<int, 4>{}); break;
+    }
+}
+
+// fp16x8 += fp16x8 (unet.py:33 `add`; the reference runs mixed_float16, so the add is an fp16 add)
 __device__ __forceinline__ uint4 add_h8(const uint4 &v, const uint4 &u) {
     const __half2 *pa = reinterpret_cast<const __half2 *>(&v);
     const __half2 *pb = reinterpret_cast<const __half2 *>(&u);
     uint4 r4;
     __half2 *ro = reinterpret_cast<__half2 *>(&r4);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float2 fa = __half22float2(pa[e]), fb = __half22float2(pb[e]);
-        ro[e] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
-    }
+    for (int e = 0; e < 4; ++e) ro[e] = __hadd2(pa[e], pb[e]);
     return r4;
 }
 
@@ -154,11 +188,11 @@ __device__ __forceinline__ uint4 add_h8(const uint4 &v, const uint4 &u) {
 __global__ void __launch_bounds__(kBtThreads, 1)
 block_tc_kernel(const __grid_constant__ BtArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    float *par = reinterpret_cast<float *>(smem + a.par_off_b);
-    uint8_t *A0 = smem + a.a0_off, *A1 = smem + a.a1_off, *A2 = smem + a.a2_off;
+    uint8_t *A0 = smem + a.a0_off, *A1 = smem + a.a1_off, *A2 = smem + a.a2_off, *OT = smem + a.o_off;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.bar_off);
     uint64_t *ld_full = bars, *ld_empty = bars + 1, *e1_done = bars + 2, *e2_done = bars + 3, *e3_done = bars + 4, *tma_full = bars + 5;
-    uint64_t *acc1_full = bars + 6, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
+    uint64_t *o_free = bars + 6;
+    uint64_t *acc1_full = bars + 7, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kBtNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -166,7 +200,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(ld_full, kBtLoadWarps); mbar_init(ld_empty, 1); mbar_init(tma_full, 1);
+        mbar_init(ld_full, kBtLoadWarps); mbar_init(ld_empty, 1); mbar_init(tma_full, 1); mbar_init(o_free, 1);
         mbar_init(e1_done, kBtEpiWarps); mbar_init(e2_done, kBtEpiWarps); mbar_init(e3_done, kBtEpiWarps);
         for (int b = 0; b < kBtMaxBlocks; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc2_full[b], 1); mbar_init(&acc3_full[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -179,7 +213,6 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.wpk);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int i = tid; i < a.w_bytes / 16; i += kBtThreads) dst[i] = src[i];
-        for (int i = tid; i < a.par_floats; i += kBtThreads) par[i] = a.par[i];
         uint4 *z = reinterpret_cast<uint4 *>(smem + a.a0_off);
         const int zn = (a.bar_off - a.a0_off) / 16;
         for (int i = tid; i < zn; i += kBtThreads) z[i] = make_uint4(0, 0, 0, 0);
@@ -212,24 +245,19 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
                 const uint32_t par_ = (uint32_t)(i & 1);
                 if (warp == 0) BT_TL(0, i, 0);
-                for (int b = g; b < a.s1.nb; b += kBtEpiGroups) {
-                    mbar_wait(&acc1_full[b], par_);
-                    __syncwarp();
-                    tc_fence_after();
-                    const int m = b * 128 + q * 32 + lane;
-                    const int r = (int)__umulhi((unsigned)m, a.pitch_magic), c = m - r * a.pitch;
-                    const int y = y0 - 1 + r, x = x0 - 1 + c;
-                    const bool inside = r < a.Th + 2 && y >= 0 && y < a.H && x >= 0 && x < a.W;
-                    for (int c0 = 0; c0 < a.s1.n; c0 += 16) {
-                        uint32_t rr[16];
-                        tc_ld16(tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.n + c0), rr);
-                        tc_wait_ld();
-                        uint4 lo, hi;
-                        epi16(rr, par + a.s1.par_off + c0, a.s1.n, inside, lo, hi);
-                        *reinterpret_cast<uint4 *>(A1 + ((size_t)(c0 >> 3) * a.Pn1 + m) * 16) = lo;
-                        *reinterpret_cast<uint4 *>(A1 + ((size_t)((c0 >> 3) + 1) * a.Pn1 + m) * 16) = hi;
+                with_nch(a.s1.n, [&](auto nch) {
+                    for (int b = g; b < a.s1.nb; b += kBtEpiGroups) {
+                        mbar_wait(&acc1_full[b], par_);
+                        __syncwarp();
+                        tc_fence_after();
+                        const int m = b * 128 + q * 32 + lane;
+                        const int r = (int)__umulhi((unsigned)m, a.pitch_magic), c = m - r * a.pitch;
+                        const int y = y0 - 1 + r, x = x0 - 1 + c;
+                        const bool inside = r < a.Th + 2 && y >= 0 && y < a.H && x >= 0 && x < a.W;
+                        epi_block<0, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.n), inside, true,
+                                                                 A1 + (size_t)m * 16, (size_t)a.Pn1 * 16);
                     }
-                }
+                });
                 // warps without a block of their own still pace themselves on the stage (a free-running warp would
                 // arrive on e1_done for FUTURE tiles and corrupt the phase counts)
                 mbar_wait(&acc1_full[a.s1.nb - 1], par_);
@@ -239,35 +267,27 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 if (lane == 0) mbar_arrive(e1_done);
                 if (warp == 0) BT_TL(0, i, 1);
             }
-            // ---- E3(i-1): S3 accumulators -> ReLU + BN -> global
+            // ---- E3(i-1): S3 accumulators -> ReLU + BN -> output tile in shared memory ([Th][Tw][C] dense); the store
+            //      warp ships it with row-wise bulk copies, so no epilogue warp ever waits on a global store
             if (i >= 1) {
-                tile_coords(a, (long long)blockIdx.x + (i - 1) * gridDim.x, n, y0, x0);
                 const uint32_t par_ = (uint32_t)((i - 1) & 1);
-                __half *out_n = a.out + (long long)n * a.H * a.W * a.s3.n;
                 if (warp == 0) BT_TL(0, i, 2);
-                for (int b = g; b < a.s3.nb; b += kBtEpiGroups) {
-                    mbar_wait(&acc3_full[b], par_);
-                    if (warp == 0 && b == g) BT_TL(0, i, 3);
-                    __syncwarp();
-                    tc_fence_after();
-                    const int m = b * 128 + q * 32 + lane;
-                    const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
-                    const int y = y0 + ro, x = x0 + co;
-                    const bool valid = ro < a.Th && co < a.Tw && y < a.H && x < a.W;
-                    __half *dst = out_n + ((long long)y * a.W + x) * a.s3.n;
-                    for (int c0 = 0; c0 < a.s3.n; c0 += 16) {
-                        uint32_t rr[16];
-                        tc_ld16(tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n + c0), rr);
-                        tc_wait_ld();
-                        uint4 lo, hi;
-                        epi16(rr, par + a.s3.par_off + c0, a.s3.n, true, lo, hi);
-                        if (valid) {
-                            reinterpret_cast<uint4 *>(dst + c0)[0] = lo;
-                            reinterpret_cast<uint4 *>(dst + c0)[1] = hi;
-                        }
+                if (i >= 2) mbar_wait(o_free, (uint32_t)(i & 1));          // tile i-2 has left the staging tile
+                with_nch(a.s3.n, [&](auto nch) {
+                    for (int b = g; b < a.s3.nb; b += kBtEpiGroups) {
+                        mbar_wait(&acc3_full[b], par_);
+                        if (warp == 0 && b == g) BT_TL(0, i, 3);
+                        __syncwarp();
+                        tc_fence_after();
+                        const int m = b * 128 + q * 32 + lane;
+                        const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
+                        const bool valid = ro < a.Th && co < a.Tw;
+                        epi_block<2, decltype(nch)::value, false>(a, tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, valid,
+                                                                  OT + ((size_t)(ro * a.Tw + co) * a.s3.n) * 2, 0);
                     }
-                }
+                });
                 mbar_wait(&acc3_full[a.s3.nb - 1], par_);
+                fence_async_smem();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(e3_done);
@@ -276,22 +296,17 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             // ---- E2(i): S2 accumulators -> ReLU -> A2 (flat layout, every row written)
             if (i < n_my) {
                 const uint32_t par_ = (uint32_t)(i & 1);
-                for (int b = g; b < a.s2.nb; b += kBtEpiGroups) {
-                    mbar_wait(&acc2_full[b], par_);
-                    if (warp == 0 && b == g) BT_TL(0, i, 5);
-                    __syncwarp();
-                    tc_fence_after();
-                    const int m = b * 128 + q * 32 + lane;
-                    for (int c0 = 0; c0 < a.s2.n; c0 += 16) {
-                        uint32_t rr[16];
-                        tc_ld16(tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n + c0), rr);
-                        tc_wait_ld();
-                        uint4 lo, hi;
-                        epi16(rr, par + a.s2.par_off + c0, a.s2.n, true, lo, hi);
-                        *reinterpret_cast<uint4 *>(A2 + ((size_t)(c0 >> 3) * a.Pn2 + m) * 16) = lo;
-                        *reinterpret_cast<uint4 *>(A2 + ((size_t)((c0 >> 3) + 1) * a.Pn2 + m) * 16) = hi;
+                with_nch(a.s2.n, [&](auto nch) {
+                    for (int b = g; b < a.s2.nb; b += kBtEpiGroups) {
+                        mbar_wait(&acc2_full[b], par_);
+                        if (warp == 0 && b == g) BT_TL(0, i, 5);
+                        __syncwarp();
+                        tc_fence_after();
+                        const int m = b * 128 + q * 32 + lane;
+                        epi_block<1, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n), true, true,
+                                                                 A2 + (size_t)m * 16, (size_t)a.Pn2 * 16);
                     }
-                }
+                });
                 mbar_wait(&acc2_full[a.s2.nb - 1], par_);
                 fence_async_smem();
                 tc_fence_before();
@@ -426,6 +441,30 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             __syncwarp();
             BT_TL(1, i, 7);
         }
+    } else if (warp == kBtEpiWarps + 1 + kBtLoadWarps) {
+        // =====================================================================================
+        //  store warp: the finished output tile leaves shared memory as one bulk copy per image row
+        // =====================================================================================
+        const uint32_t row_smem = (uint32_t)(a.Tw * a.s3.n * 2);
+        for (long long i = 0; i < n_my; ++i) {
+            int n, y0, x0;
+            tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
+            mbar_wait(e3_done, (uint32_t)(i & 1));
+            if (elect_one()) {
+                const uint32_t bytes = (uint32_t)(min(a.Tw, a.W - x0) * a.s3.n * 2);
+                __half *g0 = a.out + (((long long)n * a.H + y0) * a.W + x0) * a.s3.n;
+                const int rows = min(a.Th, a.H - y0);
+                for (int ro = 0; ro < rows; ++ro)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(g0 + (long long)ro * a.W * a.s3.n), "r"(smem_u32(OT) + (uint32_t)ro * row_smem), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(o_free);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
     } else {
         // =====================================================================================
         //  loaders
@@ -515,33 +554,66 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                         *reinterpret_cast<uint4 *>(buf + ((size_t)Pn + f) * 16) = reinterpret_cast<const uint4 *>(v)[1];
                     }
                 }
-            } else {
+            } else if (a.load_kind == 1) {
                 // the haloed tile: one TMA box per 8-channel plane, zero filled outside the image
-                const int yl0 = (y0 - 1) >> 1, xl0 = (x0 - 1) >> 1;
                 if (first && elect_one()) {
-                    const uint32_t tile_bytes = (uint32_t)KC * 16u * (uint32_t)npos;
-                    const uint32_t lo_bytes = a.load_kind == 2 ? (uint32_t)KC * 16u * (uint32_t)(a.pl_box * a.rl_box) : 0u;
-                    mbar_expect_tx(tma_full, tile_bytes + lo_bytes);
+                    mbar_expect_tx(tma_full, (uint32_t)KC * 16u * (uint32_t)npos);
                     const uint32_t dst = smem_u32(buf);
                     for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, tma_full);
-                    if (a.load_kind == 2) {
-                        const uint32_t dlo = smem_u32(smem + a.lo_off);
-                        for (int kc = 0; kc < KC; ++kc) tma_load_4d(dlo + (uint32_t)(kc * a.Pl) * 16u, &a.tm_lo, kc * 8, xl0, yl0, n, tma_full);
-                    }
                 }
                 __syncwarp();
                 mbar_wait(tma_full, (uint32_t)(i & 1));
-                if (a.load_kind == 2) {
-                    // nearest-upsample-2x(lo) + skip (unet.py:32-33), in place: fp32 add, one rounding
-                    const uint8_t *lo_s = smem + a.lo_off;
-                    const int items = npos * KC;
-                    for (int it = lt; it < items; it += NL) {
-                        const int kc = it / npos, f = it - kc * npos;
-                        const int r = (int)__umulhi((unsigned)f, a.pitch_magic), c = f - r * a.pitch;
-                        const int yl = ((y0 - 1 + r) >> 1) - yl0, xl = ((x0 - 1 + c) >> 1) - xl0;
-                        uint4 *p = reinterpret_cast<uint4 *>(buf + ((size_t)kc * Pn + f) * 16);
-                        const uint4 u = *reinterpret_cast<const uint4 *>(lo_s + ((size_t)kc * a.Pl + yl * a.pl_box + xl) * 16);
-                        *p = add_h8(*p, u);
+            } else {
+                // skip tile -> operand planes, half-resolution tile -> staging, both as 16-byte cp.async (zero fill outside
+                // the maps; every item of the tile in flight at once), then nearest-upsample-2x + add in place (unet.py:32-33)
+                const int yl0 = (y0 - 1) >> 1, xl0 = (x0 - 1) >> 1;
+                const __half *in_n = reinterpret_cast<const __half *>(a.in) + (long long)n * a.H * a.W * a.ld_cp;
+                const __half *lo_n = a.in_lo + (long long)n * (a.H >> 1) * (a.W >> 1) * a.ld_cp;
+                const uint32_t dst0 = smem_u32(buf), dlo0 = smem_u32(smem + a.lo_off);
+                const int rows = a.Th + 2, Hl = a.H >> 1, Wl = a.W >> 1;
+                // a thread owns a (column, 8-channel plane) pair and walks down the rows: one predicate and one
+                // pointer increment per 16-byte item instead of a division chain
+                for (int cc = lt; cc < a.pitch * KC; cc += NL) {
+                    const int c = cc / KC, kc = cc - c * KC;                 // plane fastest: a pixel's planes are contiguous in global memory
+                    const int x = x0 - 1 + c;
+                    const bool col_ok = x >= 0 && x < a.W;
+                    const __half *src = in_n + ((long long)(y0 - 1) * a.W + x) * a.ld_cp + kc * 8;
+                    uint32_t dst = dst0 + (uint32_t)(kc * Pn + c) * 16u;
+                    for (int r = 0; r < rows; ++r, src += (long long)a.W * a.ld_cp, dst += (uint32_t)a.pitch * 16u) {
+                        const int y = y0 - 1 + r;
+                        const bool inside = col_ok && y >= 0 && y < a.H;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(inside ? src : in_n), "r"(inside ? 16 : 0) : "memory");
+                    }
+                }
+                for (int cc = lt; cc < a.pl_box * KC; cc += NL) {
+                    const int c = cc / KC, kc = cc - c * KC;
+                    const int x = xl0 + c;
+                    const bool col_ok = x >= 0 && x < Wl;
+                    const __half *src = lo_n + ((long long)yl0 * Wl + x) * a.ld_cp + kc * 8;
+                    uint32_t dst = dlo0 + (uint32_t)(kc * a.Pl + c) * 16u;
+                    for (int r = 0; r < a.rl_box; ++r, src += (long long)Wl * a.ld_cp, dst += (uint32_t)a.pl_box * 16u) {
+                        const int y = yl0 + r;
+                        const bool inside = col_ok && y >= 0 && y < Hl;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(inside ? src : lo_n), "r"(inside ? 16 : 0) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (first) BT_TL(2, i, 3);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (first) BT_TL(2, i, 4);
+                asm volatile("bar.sync 1, %0;" :: "n"(kBtLoadWarps * 32) : "memory");      // every loader's copies have landed
+                if (first) BT_TL(2, i, 5);
+                // in-place add: a thread owns a (plane, column) pair (column fastest: conflict-free shared-memory accesses);
+                // one half-resolution value serves two consecutive rows
+                const uint8_t *lo_s = smem + a.lo_off;
+                for (int cc = lt; cc < a.pitch * KC; cc += NL) {
+                    const int kc = cc / a.pitch, c = cc - kc * a.pitch;
+                    const int xl = ((x0 - 1 + c) >> 1) - xl0;
+                    uint4 *p = reinterpret_cast<uint4 *>(buf + ((size_t)kc * Pn + c) * 16);
+                    const uint4 *ql = reinterpret_cast<const uint4 *>(lo_s + ((size_t)kc * a.Pl + xl) * 16);
+                    for (int r = 0; r < rows; ++r, p += a.pitch) {
+                        const int yl = ((y0 - 1 + r) >> 1) - yl0;
+                        *p = add_h8(*p, ql[yl * a.pl_box]);
                     }
                 }
             }
@@ -591,20 +663,21 @@ static void pack_front_b(std::vector<__half> &dst, const float *w /*[c][cout]*/,
         }
 }
 
-struct HostLayer {                      // what imk_unet_create hands over per convolution
-    const float *hwio, *bias, *bn_scale, *bn_shift;   // bn_* may be null; host pointers (scale / shift already folded)
-    int ks, cin, cout;
-};
-
-static void append_par(std::vector<float> &par, const HostLayer &L, int n) {
-    const size_t base = par.size();
-    par.resize(base + 3 * (size_t)n, 0.f);
-    for (int i = 0; i < L.cout; ++i) {
-        par[base + i] = L.bias[i];
-        par[base + n + i] = L.bn_scale ? L.bn_scale[i] : 1.f;
-        par[base + 2 * n + i] = L.bn_shift ? L.bn_shift[i] : 0.f;
+// BN scale folded into the weights (see BtArgs::cpar): returns the scaled HWIO kernel and fills cpar[stage]
+static std::vector<float> fold_stage(const ConvHost &L, int n, float (&cpar)[3][64]) {
+    const int taps = L.ks * L.ks;
+    std::vector<float> w(L.hwio, L.hwio + (size_t)taps * L.cin * L.cout);
+    const float inf = INFINITY;
+    for (int co = 0; co < 64; ++co) { cpar[0][co] = 0.f; cpar[1][co] = 0.f; cpar[2][co] = inf; }     // padding channels stay 0
+    for (int co = 0; co < L.cout; ++co) {
+        const float sc = L.bn_scale ? L.bn_scale[co] : 1.f, sh = L.bn_shift ? L.bn_shift[co] : 0.f;
+        for (size_t i = co; i < w.size(); i += L.cout) w[i] *= sc;
+        cpar[0][co] = sc * L.bias[co] + sh;
+        cpar[1][co] = sc > 0.f ? sh : (sc < 0.f ? -inf : sh);
+        cpar[2][co] = sc > 0.f ? inf : sh;
     }
-    for (int i = L.cout; i < n; ++i) par[base + n + i] = 1.f;      // padding channels: relu(0) * 1 + 0 = 0
+    (void)n;
+    return w;
 }
 
 static bool bt_disabled() {
@@ -640,6 +713,7 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, BtGeom &g) {
     off += (size_t)g.Pn1 * (a.s2.ksteps * 2) * 16;
     off += (size_t)g.Pn2 * (a.s3.ksteps * 2) * 16;
     if (a.load_kind == 2) off += (size_t)g.Pl * (a.ld_cp / 8) * 16;
+    off += ((size_t)th * tw * n3 * 2 + 127) / 128 * 128;
     if (a.load_kind == 0) off += 1024;
     off += (size_t)kBtNumBars * 8 + 16;
     g.bytes = off;
@@ -681,6 +755,7 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     a.a1_off = (int)off; off += (size_t)a.Pn1 * (a.s2.ksteps * 2) * 16;
     a.a2_off = (int)off; off += (size_t)a.Pn2 * (a.s3.ksteps * 2) * 16;
     a.lo_off = (int)off; if (a.load_kind == 2) off += (size_t)a.Pl * (a.ld_cp / 8) * 16;
+    a.o_off = (int)off; off += ((size_t)a.Th * a.Tw * a.s3.n * 2 + 127) / 128 * 128;
     a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
     a.bar_off = (int)off; off += (size_t)kBtNumBars * 8 + 16;        // everything in [a0_off, bar_off) starts zeroed
     fb.smem = off;
@@ -736,17 +811,19 @@ int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W,
     if (const char *v = getenv("IMK_BT_KINDS"); v && v[0] && !((atoi(v) >> kind) & 1)) return IMK_OK;   // debug: bitmask of fused kinds
     BtArgs &a = fb.args;
     std::vector<__half> w;
-    std::vector<float> par;
+    std::vector<float> par(4, 0.f);
     auto stage = [&](BtStage &s, const ConvHost &c, bool front) {
         const int cin_p = front ? 16 : pad_ch(c.cin), n = pad_ch(c.cout);
         s.taps = front ? 1 : c.ks * c.ks; s.ksteps = cin_p / 16; s.n = n;
         s.w_off = (int)(w.size() * sizeof(__half));
-        if (front) pack_front_b(w, c.hwio, c.cin, c.cout, n); else pack_umma_b(w, c.hwio, c.ks, c.cin, c.cout, cin_p, n);
-        s.par_off = (int)par.size();
-        HostLayer hl{c.hwio, c.bias, c.bn_scale, c.bn_shift, c.ks, c.cin, c.cout};
-        append_par(par, hl, n);
+        const int si = &s == &a.s1 ? 0 : (&s == &a.s2 ? 1 : 2);
+        const std::vector<float> ws = fold_stage(c, n, a.cpar[si]);
+        if (front) pack_front_b(w, ws.data(), c.cin, c.cout, n); else pack_umma_b(w, ws.data(), c.ks, c.cin, c.cout, cin_p, n);
+        s.par_off = 0;
     };
     a.load_kind = kind; a.in_c = in_c;
+    for (int j = 0; j < (kind == 1 ? 2 : 3); ++j)
+        if (pad_ch(L[j].cout) > 64) return IMK_OK;            // BtArgs::cpar holds 64 channels per stage
     if (kind == 1) {
         if (L[0].ks != 3 || L[1].ks != 1) return IMK_OK;
         a.has_s1 = 0;
@@ -778,10 +855,9 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
     a.in = in; a.in_lo = in_lo; a.out = out; a.swap_rb = swap_rb; a.in_f32 = in_f32;
     a.n_tiles = (long long)n * a.tiles_x * a.tiles_y;
     if (a.n_tiles <= 0) return IMK_OK;
-    if (a.load_kind != 0) {
+    if (a.load_kind == 1) {
         int rc = make_map(&a.tm_in, in, n, a.H, a.W, a.ld_cp, a.pitch, a.Th + 2);
         if (rc) return rc;
-        if (a.load_kind == 2 && (rc = make_map(&a.tm_lo, in_lo, n, a.H / 2, a.W / 2, a.ld_cp, a.pl_box, a.rl_box))) return rc;
     }
     static bool attr_set = false;
     if (!attr_set) {

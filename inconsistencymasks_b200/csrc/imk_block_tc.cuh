@@ -32,9 +32,14 @@ struct BtArgs {
     int par_off_b, a0_off, a1_off, a2_off, bar_off; // byte offsets in dynamic shared memory
     unsigned pitch_magic;               // ceil(2^32 / pitch)
     int lo_off, Pl, pl_box, rl_box;     // DEC: staging of the half-resolution tile ([kc][rl_box * pl_box (+pad)][8 ch])
+    int o_off;                          // output staging tile [Th][Tw][Cout] fp16
     int lut_off;                        // FRONT: 256-entry table of x/255 as fp16 hi | lo << 16
     alignas(64) CUtensorMap tm_in;      // TMA maps (ENC / DEC): {8 ch, pitch, Th + 2, 1} boxes of the fp16 NHWC input ...
     alignas(64) CUtensorMap tm_lo;      // ... and {8 ch, pl_box, rl_box, 1} boxes of the half-resolution map
+    // Epilogue constants, read as constant-bank operands (no loads): the BN scale is folded into the weights, so a
+    // stage's epilogue is  v = acc + cpar[s][0][c];  v = min(max(v, cpar[s][1][c]), cpar[s][2][c])
+    //   scale > 0: (b', lo, hi) = (scale*bias + shift, shift, +inf)   scale < 0: (.., -inf, shift)   ReLU only: (bias, 0, +inf)
+    float cpar[3][3][64];
     long long *dbg;                     // optional timeline buffer (IMK_BT_TIMELINE=1): [3 roles][16 tiles][8 events] clocks of CTA 0
 };
 
