@@ -69,8 +69,17 @@ def layer_work(n_images):
             in_b += px // 4 * pad(cin) * 2
         out_b = px * (cout * 4 if last else pad(cout) * 2)
         out.append(dict(layer=i, ks=ks, cin=cin, cout=cout, level=lvl, bytes=in_b + out_b + ks * ks * cin * cout * 2,
-                        flops=2.0 * px * ks * ks * cin * cout))
+                        in_bytes=in_b, out_bytes=out_b, w_bytes=ks * ks * cin * cout * 2, flops=2.0 * px * ks * ks * cin * cout))
     return out
+
+
+def block_work(work, kernel, tag):
+    """Algorithmic work of a block-fused kernel: it reads the first layer's input and writes the last layer's output
+    (the maps in between never leave the SM); flops are those of every fused convolution."""
+    n = {"block_front": 3, "block_enc": 2, "block_dec": 3}[kernel]
+    layers = [work[tag + j] for j in range(n)]
+    return dict(bytes=layers[0]["in_bytes"] + layers[-1]["out_bytes"] + sum(l["w_bytes"] for l in layers),
+                flops=sum(l["flops"] for l in layers))
 
 
 def im_bytes_per_image():
@@ -258,10 +267,10 @@ def run_b200(args, rank, local_rank, world):
         check(lib.imk_pseudo_label_binary_host(handles, M, h_img.data_ptr(), Ne, 0.5, 0, 1, 1, h_out.data_ptr(), h_lab.data_ptr(),
                                                h_im.data_ptr(), h_sz.data_ptr(), h_pred.data_ptr(), args.e2e_chunk))
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
-    e2e_steps = max(1, args.steps // 2)
+    e2e_steps = max(2, args.steps)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -294,8 +303,8 @@ def run_b200(args, rank, local_rank, world):
     for p in sorted(prof, key=lambda p: -p["total_ms"]):
         avg_ms = p["total_ms"] / p["launches"]
         row = dict(kernel=p["name"], layer=p["tag"], launches=p["launches"], avg_us=1e3 * avg_ms, share=p["total_ms"] / total_ms)
-        if p["tag"] in work and p["name"].startswith(("conv", "in_conv")):
-            wk = work[p["tag"]]
+        if p["tag"] in work and p["name"].startswith(("conv", "in_conv", "block_")):
+            wk = block_work(work, p["name"], p["tag"]) if p["name"].startswith("block_") else work[p["tag"]]
             row.update(gbs=wk["bytes"] / avg_ms / 1e6, tflops=wk["flops"] / avg_ms / 1e9, bytes=wk["bytes"], flops=wk["flops"])
         rows.append(row)
     top = rows[0]

@@ -108,26 +108,69 @@ extern "C" int imk_profile_end(imk_profile_entry *out, int cap, int *n_out) {
 // ---------------------------------------------------------------------------------------
 namespace {
 
+// Device-side staging of the host pipeline.  Allocated once per thread and grown on demand (no cudaMalloc /
+// cudaFree -- both synchronise the device -- on the per-directory call path); three slots so that the upload of
+// chunk i+1, the kernels of chunk i and the download of chunk i-1 overlap on three streams / two copy engines.
+constexpr int kSlots = 3;
+
 struct Slot {
-    cudaStream_t stream = nullptr;
     uint8_t *img = nullptr, *img_out = nullptr, *labels = nullptr, *im = nullptr;
     int64_t *im_size = nullptr, *pred_size = nullptr;
     uint8_t *lists_equal = nullptr;
+    cudaEvent_t up_done = nullptr, comp_done = nullptr, down_done = nullptr;
 };
 
 struct Pipeline {
-    Slot slot[2];
-    int64_t chunk = 0;
-    size_t img_bytes = 0;
-    int planes = 0;
-    ~Pipeline() {
+    Slot slot[kSlots];
+    cudaStream_t up = nullptr, compute = nullptr, down = nullptr;
+    size_t cap_img = 0, cap_px = 0, cap_lab = 0;
+    int64_t cap_chunk = 0;
+    int device = -1;
+    void release() {
         for (Slot &s : slot) {
-            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
             cudaFree(s.img); cudaFree(s.img_out); cudaFree(s.labels); cudaFree(s.im);
             cudaFree(s.im_size); cudaFree(s.pred_size); cudaFree(s.lists_equal);
+            if (s.up_done) cudaEventDestroy(s.up_done);
+            if (s.comp_done) cudaEventDestroy(s.comp_done);
+            if (s.down_done) cudaEventDestroy(s.down_done);
+            s = Slot{};
         }
+        if (up) cudaStreamDestroy(up);
+        if (compute) cudaStreamDestroy(compute);
+        if (down) cudaStreamDestroy(down);
+        up = compute = down = nullptr;
+        cap_img = cap_px = cap_lab = 0; cap_chunk = 0;
     }
+    ~Pipeline() { release(); }
 };
+
+static thread_local Pipeline g_pipe;
+
+int pipeline_reserve(Pipeline &P, int64_t chunk, size_t img_bytes, size_t px_bytes, size_t lab_bytes, int planes) {
+    int dev = 0;
+    IMK_CUDA(cudaGetDevice(&dev));
+    if (P.device == dev && P.cap_chunk >= chunk && P.cap_img >= img_bytes && P.cap_px >= px_bytes && P.cap_lab >= lab_bytes) return IMK_OK;
+    IMK_CUDA(cudaDeviceSynchronize());
+    P.release();
+    P.device = dev;
+    IMK_CUDA(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
+    IMK_CUDA(cudaStreamCreateWithFlags(&P.compute, cudaStreamNonBlocking));
+    IMK_CUDA(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+    for (Slot &s : P.slot) {
+        IMK_CUDA(cudaMalloc(&s.img, img_bytes));
+        IMK_CUDA(cudaMalloc(&s.img_out, img_bytes));
+        IMK_CUDA(cudaMalloc(&s.labels, lab_bytes));
+        IMK_CUDA(cudaMalloc(&s.im, px_bytes));
+        IMK_CUDA(cudaMalloc(&s.im_size, sizeof(int64_t) * chunk));
+        IMK_CUDA(cudaMalloc(&s.pred_size, sizeof(int64_t) * chunk * (planes > 3 ? planes : 3)));
+        IMK_CUDA(cudaMalloc(&s.lists_equal, (size_t)chunk));
+        IMK_CUDA(cudaEventCreateWithFlags(&s.up_done, cudaEventDisableTiming));
+        IMK_CUDA(cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming));
+        IMK_CUDA(cudaEventCreateWithFlags(&s.down_done, cudaEventDisableTiming));
+    }
+    P.cap_chunk = chunk; P.cap_img = img_bytes; P.cap_px = px_bytes; P.cap_lab = lab_bytes;
+    return IMK_OK;
+}
 
 int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images, int64_t N,
                       float thr, int strict, int block_in, int block_out,
@@ -140,66 +183,46 @@ int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uin
     const int64_t HW = (int64_t)d.height * d.width;
     const int K = d.num_outputmasks;
     const int planes = multiclass ? 1 : K;
-    if (chunk <= 0) chunk = kMaxChunk;
+    if (chunk <= 0) chunk = 4 * kMaxChunk;
     chunk = std::min<int64_t>(chunk, N);
-    // Each model keeps ONE workspace, so the two slots serialise on the compute stream
-    // order: kernels of consecutive chunks are issued to a single compute stream while the
-    // uploads / downloads run on the slot streams, ordered by events.
-    Pipeline P;
-    P.chunk = chunk;
-    cudaStream_t compute = nullptr;
-    IMK_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
-    struct ComputeGuard { cudaStream_t s; ~ComputeGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } guard{compute};
-    cudaEvent_t up_done[2], comp_done[2], down_done[2];
-    for (int s = 0; s < 2; ++s) {
-        IMK_CUDA(cudaStreamCreateWithFlags(&P.slot[s].stream, cudaStreamNonBlocking));
-        IMK_CUDA(cudaMalloc(&P.slot[s].img, (size_t)chunk * HW * d.in_channels));
-        IMK_CUDA(cudaMalloc(&P.slot[s].img_out, (size_t)chunk * HW * d.in_channels));
-        IMK_CUDA(cudaMalloc(&P.slot[s].labels, (size_t)chunk * HW * planes));
-        IMK_CUDA(cudaMalloc(&P.slot[s].im, (size_t)chunk * HW));
-        IMK_CUDA(cudaMalloc(&P.slot[s].im_size, sizeof(int64_t) * chunk));
-        IMK_CUDA(cudaMalloc(&P.slot[s].pred_size, sizeof(int64_t) * chunk * planes));
-        IMK_CUDA(cudaMalloc(&P.slot[s].lists_equal, (size_t)chunk));
-        IMK_CUDA(cudaEventCreateWithFlags(&up_done[s], cudaEventDisableTiming));
-        IMK_CUDA(cudaEventCreateWithFlags(&comp_done[s], cudaEventDisableTiming));
-        IMK_CUDA(cudaEventCreateWithFlags(&down_done[s], cudaEventDisableTiming));
-    }
-    struct EvGuard { cudaEvent_t *a, *b, *c; ~EvGuard() { for (int s = 0; s < 2; ++s) { cudaEventDestroy(a[s]); cudaEventDestroy(b[s]); cudaEventDestroy(c[s]); } } } evg{up_done, comp_done, down_done};
-
+    Pipeline &P = g_pipe;
+    int rc = pipeline_reserve(P, chunk, (size_t)chunk * HW * d.in_channels, (size_t)chunk * HW, (size_t)chunk * HW * planes, planes);
+    if (rc) return rc;
+    // Each model keeps ONE workspace, so the kernels of consecutive chunks are issued to a single compute stream;
+    // uploads and downloads run on their own streams, ordered by events.
     const int64_t n_chunks = (N + chunk - 1) / chunk;
-    int rc = IMK_OK;
     for (int64_t i = 0; i < n_chunks; ++i) {
-        const int s = (int)(i & 1);
-        Slot &S = P.slot[s];
+        Slot &S = P.slot[i % kSlots];
         const int64_t n0 = i * chunk, n = std::min<int64_t>(chunk, N - n0);
-        // slot buffers are free again once chunk i-2's download has finished
-        if (i >= 2) IMK_CUDA(cudaStreamWaitEvent(S.stream, down_done[s], 0));
-        IMK_CUDA(cudaMemcpyAsync(S.img, images + n0 * HW * d.in_channels, (size_t)n * HW * d.in_channels, cudaMemcpyHostToDevice, S.stream));
-        IMK_CUDA(cudaEventRecord(up_done[s], S.stream));
-        IMK_CUDA(cudaStreamWaitEvent(compute, up_done[s], 0));
+        // the slot is free again once chunk i - kSlots has been downloaded
+        if (i >= kSlots) IMK_CUDA(cudaStreamWaitEvent(P.up, S.down_done, 0));
+        IMK_CUDA(cudaMemcpyAsync(S.img, images + n0 * HW * d.in_channels, (size_t)n * HW * d.in_channels, cudaMemcpyHostToDevice, P.up));
+        IMK_CUDA(cudaEventRecord(S.up_done, P.up));
+        IMK_CUDA(cudaStreamWaitEvent(P.compute, S.up_done, 0));
+        if (i >= kSlots) IMK_CUDA(cudaStreamWaitEvent(P.compute, S.down_done, 0));
         if (multiclass)
             rc = imk_ensemble_im_multiclass(nets, M, S.img, n, block_in, block_out, img_out ? S.img_out : nullptr, S.labels, S.im,
-                                            S.im_size, lists_equal ? S.lists_equal : nullptr, compute);
+                                            S.im_size, lists_equal ? S.lists_equal : nullptr, P.compute);
         else
             rc = imk_ensemble_im_binary(nets, M, S.img, n, thr, strict, block_in, block_out, img_out ? S.img_out : nullptr, S.labels,
-                                        S.im, S.im_size, pred_size ? S.pred_size : nullptr, compute);
-        if (rc) return rc;
-        IMK_CUDA(cudaEventRecord(comp_done[s], compute));
-        IMK_CUDA(cudaStreamWaitEvent(S.stream, comp_done[s], 0));
-        if (img_out) IMK_CUDA(cudaMemcpyAsync(img_out + n0 * HW * d.in_channels, S.img_out, (size_t)n * HW * d.in_channels, cudaMemcpyDeviceToHost, S.stream));
+                                        S.im, S.im_size, pred_size ? S.pred_size : nullptr, P.compute);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        IMK_CUDA(cudaEventRecord(S.comp_done, P.compute));
+        IMK_CUDA(cudaStreamWaitEvent(P.down, S.comp_done, 0));
+        if (img_out) IMK_CUDA(cudaMemcpyAsync(img_out + n0 * HW * d.in_channels, S.img_out, (size_t)n * HW * d.in_channels, cudaMemcpyDeviceToHost, P.down));
         if (labels)
             for (int k = 0; k < planes; ++k)     // slot planes are n*HW apart, host planes N*HW apart
-                IMK_CUDA(cudaMemcpyAsync(labels + (int64_t)k * N * HW + n0 * HW, S.labels + (int64_t)k * n * HW, (size_t)n * HW, cudaMemcpyDeviceToHost, S.stream));
-        if (im) IMK_CUDA(cudaMemcpyAsync(im + n0 * HW, S.im, (size_t)n * HW, cudaMemcpyDeviceToHost, S.stream));
-        if (im_size) IMK_CUDA(cudaMemcpyAsync(im_size + n0, S.im_size, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, S.stream));
+                IMK_CUDA(cudaMemcpyAsync(labels + (int64_t)k * N * HW + n0 * HW, S.labels + (int64_t)k * n * HW, (size_t)n * HW, cudaMemcpyDeviceToHost, P.down));
+        if (im) IMK_CUDA(cudaMemcpyAsync(im + n0 * HW, S.im, (size_t)n * HW, cudaMemcpyDeviceToHost, P.down));
+        if (im_size) IMK_CUDA(cudaMemcpyAsync(im_size + n0, S.im_size, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, P.down));
         if (pred_size && !multiclass)
             for (int k = 0; k < planes; ++k)
-                IMK_CUDA(cudaMemcpyAsync(pred_size + (int64_t)k * N + n0, S.pred_size + (int64_t)k * n, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, S.stream));
-        if (lists_equal && multiclass) IMK_CUDA(cudaMemcpyAsync(lists_equal + n0, S.lists_equal, (size_t)n, cudaMemcpyDeviceToHost, S.stream));
-        IMK_CUDA(cudaEventRecord(down_done[s], S.stream));
+                IMK_CUDA(cudaMemcpyAsync(pred_size + (int64_t)k * N + n0, S.pred_size + (int64_t)k * n, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, P.down));
+        if (lists_equal && multiclass) IMK_CUDA(cudaMemcpyAsync(lists_equal + n0, S.lists_equal, (size_t)n, cudaMemcpyDeviceToHost, P.down));
+        IMK_CUDA(cudaEventRecord(S.down_done, P.down));
     }
-    for (int s = 0; s < 2; ++s) IMK_CUDA(cudaStreamSynchronize(P.slot[s].stream));
-    IMK_CUDA(cudaStreamSynchronize(compute));
+    IMK_CUDA(cudaStreamSynchronize(P.down));
+    IMK_CUDA(cudaStreamSynchronize(P.compute));
     return IMK_OK;
 }
 

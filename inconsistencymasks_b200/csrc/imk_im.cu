@@ -112,9 +112,10 @@ im_binary_vec_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, float 
         uint32_t im_cnt = 0;
 #pragma unroll
         for (int j = 0; j < 4 * K; ++j) im_cnt += __popc(mix01[j]);
-        const int64_t n_lo = px0 / HW;
+        const bool small = total_px < 0x7fffffffLL;              // 32-bit image index arithmetic where possible
+        const int64_t n_lo = small ? (int64_t)((uint32_t)px0 / (uint32_t)HW) : px0 / HW;
         const bool uniform = full && (px0 + kChunkPx <= (n_lo + 1) * HW);
-        const int64_t n_u = uniform ? n_lo : (live ? px / HW : -1);
+        const int64_t n_u = uniform ? n_lo : (live ? (small ? (int64_t)((uint32_t)px / (uint32_t)HW) : px / HW) : -1);
         warp_add_stat(im_size, n_u, live ? im_cnt : 0u, uniform);
         if (pred_size) {
 #pragma unroll
@@ -227,6 +228,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+template <int C>                          // image channels at compile time (1, 3, 4; 0 = run-time)
 __global__ void __launch_bounds__(kMcThreads)
 im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, int K, int n_slots,
                          const uint8_t *__restrict__ img, int c, int block_in, int block_out,
@@ -251,16 +253,16 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
     if (warp == kMcConsumers / 32) {
         // ---------------- producer: one elected lane streams (tile, model) slabs ----------------
         if (lane == 0) {
-            int64_t q = 0;                                       // running slab index of this CTA
+            int slot = 0, round = 0;                             // ring position (no divisions on the hot path)
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int64_t p0 = tile * kMcTile;
                 const int64_t pc = min((int64_t)kMcTile, total_px - p0);
                 const uint32_t bytes = (uint32_t)(pc * K * sizeof(float));
-                for (int m = 0; m < M; ++m, ++q) {
-                    const int slot = (int)(q % n_slots);
-                    if (q >= n_slots) mbar_wait(&empty[slot], (uint32_t)(((q / n_slots) - 1) & 1));
+                for (int m = 0; m < M; ++m) {
+                    if (round > 0) mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
                     mbar_expect_tx(&full[slot], bytes);
                     bulk_g2s(slots + slot * slot_floats, probs.p[m] + p0 * K, bytes, &full[slot]);
+                    if (++slot == n_slots) { slot = 0; ++round; }
                 }
             }
         }
@@ -268,19 +270,20 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
     }
 
     // ---------------- consumers: thread p owns pixel p of the tile ----------------
-    int64_t q = 0;
+    int slot = 0;
+    uint32_t phase = 0;
+    const bool small = total_px < 0x7fffffffLL;                  // 32-bit image index arithmetic (64-bit division is a subroutine)
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t p0 = tile * kMcTile;
         const int pc = (int)min((int64_t)kMcTile, total_px - p0);
         const bool live = tid < pc;
-        const int64_t n_lo = p0 / HW;
+        const int64_t n_lo = small ? (int64_t)((uint32_t)p0 / (uint32_t)HW) : p0 / HW;
         const bool uniform = (p0 + pc <= (n_lo + 1) * HW);
-        const int64_t n_px = live ? (uniform ? n_lo : (p0 + tid) / HW) : -1;
+        const int64_t n_px = live ? (uniform ? n_lo : (small ? (int64_t)((uint32_t)(p0 + tid) / (uint32_t)HW) : (p0 + tid) / HW)) : -1;
         uint32_t disagree = 0;
         int a0 = 0;
-        for (int m = 0; m < M; ++m, ++q) {
-            const int slot = (int)(q % n_slots);
-            mbar_wait(&full[slot], (uint32_t)((q / n_slots) & 1));
+        for (int m = 0; m < M; ++m) {
+            mbar_wait(&full[slot], phase);
             int arg = 0;
             if (live) {
                 arg = argmax_row(slots + slot * slot_floats + (size_t)tid * K, K);
@@ -288,6 +291,7 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);            // this warp is done with the slab
+            if (++slot == n_slots) { slot = 0; phase ^= 1u; }
             if (presence)
                 warp_or_stat(presence, n_px < 0 ? -1 : n_px * M + m, live ? (1ull << (arg & 63)) : 0ull, uniform && pc == kMcTile);
         }
@@ -307,16 +311,17 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
             stg_stream(label_out + px, *reinterpret_cast<const uint4 *>(lab_s + warp * 32 + 16 * lane));   // 0 where the IM is set
             stg_stream(im_out + px, make_uint4(imw[0], imw[1], imw[2], imw[3]));
         }
-        if (img_out && lane < 2 * c) {
-            const int g = lane / c, v = lane - g * c;            // 16-pixel group, 16-byte vector inside it
+        const int cc = C > 0 ? C : c;
+        if (img_out && lane < 2 * cc) {
+            const int g = lane >= cc ? 1 : 0, v = lane - g * cc;   // 16-pixel group, 16-byte vector inside it
             const int64_t px = wpx + 16 * g;
             if (px < p0 + pc) {
                 const uint32_t bits = block_in ? (im_mask >> (16 * g)) : 0u;
                 uint32_t imw[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(bits4_to_bytes01(bits >> (4 * j)));
-                const uint4 pix = ldg_stream(img + px * c + 16 * v);
-                stg_stream(img_out + px * c + 16 * v, blank_vec_rt(pix, imw, c, v));
+                const uint4 pix = ldg_stream(img + px * cc + 16 * v);
+                stg_stream(img_out + px * cc + 16 * v, blank_vec_sel<C>(pix, imw, cc, v));
             }
         }
         __syncwarp();
@@ -510,10 +515,15 @@ extern "C" int imk_im_multiclass(const float *const *probs_dev, int M, int64_t N
     IMK_PROFILE(tma ? "im_multiclass_tma" : "im_multiclass_generic", -1, stream);
     if (tma) {
         const size_t smem = (size_t)n_slots * slab_bytes + 8 * 32 + 2 * kMcMaxSlots * sizeof(uint64_t);
-        IMK_CUDA(cudaFuncSetAttribute(im_multiclass_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = grid_for((total + kMcTile - 1) / kMcTile, 1, per_sm);
-        im_multiclass_tma_kernel<<<grid, kMcThreads, smem, stream>>>(pp, M, total, HW, K, n_slots, img_dev, c, block_in, block_out,
-                                                                     img_out_dev, label_dev, im_dev, im_size_dev, presence);
+#define IMK_LAUNCH_MC(CC)                                                                                                          \
+        do {                                                                                                                       \
+            IMK_CUDA(cudaFuncSetAttribute(im_multiclass_tma_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            im_multiclass_tma_kernel<CC><<<grid, kMcThreads, smem, stream>>>(pp, M, total, HW, K, n_slots, img_dev, c, block_in,    \
+                                                                             block_out, img_out_dev, label_dev, im_dev, im_size_dev, presence); \
+        } while (0)
+        if (c == 3) IMK_LAUNCH_MC(3); else if (c == 1) IMK_LAUNCH_MC(1); else if (c == 4) IMK_LAUNCH_MC(4); else IMK_LAUNCH_MC(0);
+#undef IMK_LAUNCH_MC
     } else {
         const int grid = grid_for(total, 256, 8);
         im_multiclass_generic_kernel<<<grid, 256, 0, stream>>>(pp, M, total, HW, K, img_dev, c, block_in, block_out,

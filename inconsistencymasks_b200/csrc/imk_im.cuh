@@ -13,33 +13,47 @@ __device__ __forceinline__ uint32_t decide(float p, float thr, bool strict) {
 }
 
 // np.argmax (functions.py:3225): first index of the maximum, NaN is the maximum (the first NaN wins).
-// argmax_step folds candidate (v, k) into the running (best, arg); every index folded so far must be
-// smaller than k.  The rule is associative over ORDERED groups, so rows are reduced as trees of 8
-// (8 independent shared-memory loads in flight, dependency depth 4 instead of 8).
+// Floats are mapped to unsigned keys whose integer order is the float order with -0 == +0 and every NaN on top,
+// so that one strict integer compare per element implements the whole rule (about 8 instructions per element).
+__device__ __forceinline__ uint32_t order_key(float v) {
+    v = v + 0.0f;                                                   // -0 -> +0 (np.argmax: equal, the first wins)
+    const uint32_t b = __float_as_uint(v);
+    const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+    return (v != v) ? 0xFFFFFFFFu : key;
+}
+
+// argmax_step folds candidate (v, k) into the running (best, arg); every index folded so far must be smaller than k.
 __device__ __forceinline__ void argmax_step(float v, int k, float &best, int &arg) {
     // a NaN `best` can never be displaced; a NaN v displaces any non-NaN best
     if (!(best != best) && (v > best || v != v)) { best = v; arg = k; }
 }
 
-__device__ __forceinline__ int argmax_row(const float *__restrict__ row, int K) {
-    float best = 0.f;
-    int arg = 0, k = 0;
-    for (; k + 8 <= K; k += 8) {
-        float v[8];
-        int i[8];
+template <int KT>
+__device__ __forceinline__ int argmax_row_t(const float *__restrict__ row, int K) {
+    uint32_t best = order_key(row[0]);
+    int arg = 0;
+    if constexpr (KT > 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { v[e] = row[k + e]; i[e] = k + e; }
-        argmax_step(v[1], i[1], v[0], i[0]); argmax_step(v[3], i[3], v[2], i[2]);
-        argmax_step(v[5], i[5], v[4], i[4]); argmax_step(v[7], i[7], v[6], i[6]);
-        argmax_step(v[2], i[2], v[0], i[0]); argmax_step(v[6], i[6], v[4], i[4]);
-        argmax_step(v[4], i[4], v[0], i[0]);
-        if (k == 0) { best = v[0]; arg = i[0]; } else argmax_step(v[0], i[0], best, arg);
-    }
-    for (; k < K; ++k) {
-        const float v = row[k];
-        if (k == 0) { best = v; arg = 0; } else argmax_step(v, k, best, arg);
+        for (int k = 1; k < KT; ++k) {
+            const uint32_t key = order_key(row[k]);
+            if (key > best) { best = key; arg = k; }
+        }
+    } else {
+#pragma unroll 4
+        for (int k = 1; k < K; ++k) {
+            const uint32_t key = order_key(row[k]);
+            if (key > best) { best = key; arg = k; }
+        }
     }
     return arg;
+}
+
+__device__ __forceinline__ int argmax_row(const float *__restrict__ row, int K) {
+    switch (K) {                                                    // the reference's class counts (config.ini:64, 85) fully unrolled
+        case 9: return argmax_row_t<9>(row, K);
+        case 35: return argmax_row_t<35>(row, K);
+        default: return argmax_row_t<0>(row, K);
+    }
 }
 
 // ---- SIMD-within-a-word helpers on packed bytes ---------------------------------------
@@ -97,21 +111,37 @@ __device__ __forceinline__ void blank_image16_any(const uint8_t *img, uint8_t *i
     }
 }
 
-// Runtime-indexed variant for the warp-cooperative epilogues: vector q (0..c-1) of a 16-pixel group.
-__device__ __forceinline__ uint4 blank_vec_rt(uint4 v, const uint32_t (&imw)[4], int c, int q) {
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// Variant for the warp-cooperative epilogues: vector q (0..C-1, runtime) of a 16-pixel group.  With the channel
+// count known at compile time every byte selector folds to a constant (4 PRMT + 4 LOP per vector); C == 0 is the
+// generic run-time path.
+template <int C>
+__device__ __forceinline__ uint4 blank_vec_sel(uint4 v, const uint32_t (&imw)[4], int c, int q) {
+    if constexpr (C == 1) {
+        return blank_vec<1>(v, imw, 0);
+    } else if constexpr (C == 2) {
+        return q == 0 ? blank_vec<2>(v, imw, 0) : blank_vec<2>(v, imw, 1);
+    } else if constexpr (C == 3) {
+        return q == 0 ? blank_vec<3>(v, imw, 0) : (q == 1 ? blank_vec<3>(v, imw, 1) : blank_vec<3>(v, imw, 2));
+    } else if constexpr (C == 4) {
+        return q < 2 ? (q == 0 ? blank_vec<4>(v, imw, 0) : blank_vec<4>(v, imw, 1)) : (q == 2 ? blank_vec<4>(v, imw, 2) : blank_vec<4>(v, imw, 3));
+    } else {
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int i = 4 * q + j;
-        const int r = i % c;
-        uint32_t sel = 0;
+        for (int j = 0; j < 4; ++j) {
+            const int i = 4 * q + j;
+            const int r = i % c;
+            uint32_t sel = 0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) sel |= (uint32_t)((4 * r + e) / c) << (4 * e);
-        const int src = i / c;
-        const uint32_t m = src == 0 ? imw[0] : src == 1 ? imw[1] : src == 2 ? imw[2] : imw[3];
-        w[j] &= ~__byte_perm(m, 0u, sel);
+            for (int e = 0; e < 4; ++e) sel |= (uint32_t)((4 * r + e) / c) << (4 * e);
+            const int src = i / c;
+            const uint32_t m = src == 0 ? imw[0] : src == 1 ? imw[1] : src == 2 ? imw[2] : imw[3];
+            w[j] &= ~__byte_perm(m, 0u, sel);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
     }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 blank_vec_rt(uint4 v, const uint32_t (&imw)[4], int c, int q) {
+    return blank_vec_sel<0>(v, imw, c, q);
 }
 
 // Add per-lane counts into per-image int64 slots.  `n` is the lane's image index

@@ -326,9 +326,11 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p, int K, int act, float thr, int s
         uint32_t votes[NL];
 #pragma unroll
         for (int l = 0; l < NL; ++l) votes[l] = 0;
-        const bool uniform = (p0 / HW) == ((p0 + 255) / HW) && (p0 + 256 <= total_px);
-        const int64_t n = live ? px / HW : -1;
-        const int64_t n_u = uniform ? p0 / HW : n;
+        // image index: one 32-bit division per tile (the 64-bit one is a subroutine; chunks are far below 2^31 pixels)
+        const int64_t n_first = (int64_t)((uint32_t)p0 / (uint32_t)HW);
+        const bool uniform = (p0 + 256 <= (n_first + 1) * HW) && (p0 + 256 <= total_px);
+        const int64_t n = live ? (uniform ? n_first : (int64_t)((uint32_t)px / (uint32_t)HW)) : -1;
+        const int64_t n_u = uniform ? n_first : n;
         for (int m = 0; m < M; ++m) {
             int arg = 0;
             if (live) {

@@ -287,6 +287,41 @@ def test_im_multiclass_vs_oracle(lib, shape, K, M):
     same(out2, img)
 
 
+@pytest.mark.parametrize("K", [9, 35, 5])
+def test_argmax_edge_semantics(lib, K):
+    """np.argmax corner cases (functions.py:3225): exact ties -> first index, -0.0 == +0.0, NaN is the maximum and the
+    first NaN wins, infinities, negative values (the C ABI accepts any float32 map, not only softmax outputs)."""
+    rng = np.random.default_rng(K)
+    h, w = 16, 16
+    p = rng.standard_normal((1, h, w, K)).astype(np.float32)
+    flat = p.reshape(-1, K)
+    flat[0] = 0.0                                    # all equal
+    flat[1] = 0.0; flat[1, 2] = -0.0; flat[1, 3] = 0.0
+    flat[2] = -0.0; flat[2, 4] = 0.0                 # +0 after -0: still a tie, the first wins
+    flat[3] = -1.0; flat[3, K - 1] = -0.0            # -0 is the maximum of negatives
+    flat[4, 1] = np.nan
+    flat[5, 1] = np.inf; flat[5, 3] = np.nan         # NaN beats +inf
+    flat[6, 2] = np.nan; flat[6, 4] = np.nan         # the first NaN wins
+    flat[7] = -np.inf; flat[7, 3] = -3.0e38
+    flat[8] = np.inf                                 # ties at +inf
+    flat[9] = 1.0; flat[9, K - 1] = np.nextafter(np.float32(1), np.float32(2))
+    flat[10] = np.float32(1e-45)                     # denormals
+    flat[10, 2] = np.float32(3e-45)
+    flat[11, 0] = np.nan
+    flat[12] = np.nan
+    flat[13] = -5.0; flat[13, 1] = -4.0; flat[13, 2] = -4.0
+    img = rng.integers(0, 256, size=(1, h, w, 3), dtype=np.uint8)
+    out, lab, im, sz, _ = _call_im_multiclass(lib, [p], img, 1, 1, False)
+    same(lab[0], np.argmax(p[0], axis=-1).astype(np.uint8))
+    assert sz[0] == 0 and not im.any()
+    # two models that differ exactly where the corner cases sit
+    p2 = p.copy(); p2.reshape(-1, K)[:14] = np.roll(flat[:14], 1, axis=-1)
+    out, lab, im, sz, _ = _call_im_multiclass(lib, [p, p2], img, 1, 1, False)
+    e_lab, e_im, e_sz, _ = ref_im.im_prediction_multiclass([p[0], p2[0]], False)
+    same(lab[0], e_lab); same(im[0], e_im)
+    assert sz[0] == e_sz
+
+
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7])
 def test_morphology_vs_cv2(lib, k):
     rng = np.random.default_rng(k)
