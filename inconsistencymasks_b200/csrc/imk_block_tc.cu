@@ -40,12 +40,17 @@
 
 namespace imk {
 
-constexpr int kBtEpiWarps = 16;
-constexpr int kBtEpiGroups = kBtEpiWarps / 4;
-constexpr int kBtLoadWarps = 8;
-constexpr int kBtThreads = (kBtEpiWarps + 1 + kBtLoadWarps + 1) * 32;    // + one store warp
+// Two launch shapes of the same kernel (template <EW epilogue warps, LW loader warps>, + 1 MMA warp + 1 store warp):
+//   <16, 8>  832 threads, 1 CTA / SM, up to 512 TMEM columns and 227 KB of shared memory
+//   < 8, 4>  448 threads, 2 CTAs / SM, up to 256 TMEM columns and 112 KB each: two independent tile pipelines share
+//            the SM, so one CTA's tensor-pipe work fills the other's epilogue / load hand-off bubbles
+// suspend-time hint of the mbarrier waits: a waiting warp sleeps in hardware (and is woken by the phase flip) instead of
+// re-issuing try_wait -- the polling instructions of 20+ waiting warps otherwise take a quarter of the issue slots
+constexpr uint32_t kBtSuspendNs = 20000;
 constexpr int kBtSmemMax = 227 * 1024;
-constexpr int kBtNumBars = 7 + 3 * kBtMaxBlocks;
+constexpr int kBtSmemMax2 = 112 * 1024;
+constexpr int bt_threads(int ew, int lw) { return (ew + 1 + lw + 1) * 32; }
+constexpr int kBtNumBars = 10 + 3 * kBtMaxBlocks;
 
 namespace {
 
@@ -70,11 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}"
-        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+        :: "r"(smem_u32(bar)), "r"(parity), "r"(kBtSuspendNs) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -120,14 +125,17 @@ __device__ __forceinline__ void tile_coords(const BtArgs &a, long long tile, int
 // is a constant-bank operand of the FADD / FMNMX itself (BtArgs is __grid_constant__): no loads, no registers.
 template <int STAGE, int CH>
 __device__ __forceinline__ void epi16(const BtArgs &a, const uint32_t (&r)[16], bool keep, uint4 &lo, uint4 &hi) {
+    // v = acc + b' in fp32, ONE rounding to fp16, then the clamp on packed halves: rounding is monotonic, so
+    // clamp(round(v), round(lo), round(hi)) == round(clamp(v, lo, hi)) bit for bit, at half the instructions.  The
+    // upper bound exists only for BN channels with a negative scale (a.has_hi: uniform per stage).
     uint32_t o[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        float v0 = __uint_as_float(r[2 * q]) + a.cpar[STAGE][0][16 * CH + 2 * q];
-        float v1 = __uint_as_float(r[2 * q + 1]) + a.cpar[STAGE][0][16 * CH + 2 * q + 1];
-        v0 = fminf(fmaxf(v0, a.cpar[STAGE][1][16 * CH + 2 * q]), a.cpar[STAGE][2][16 * CH + 2 * q]);
-        v1 = fminf(fmaxf(v1, a.cpar[STAGE][1][16 * CH + 2 * q + 1]), a.cpar[STAGE][2][16 * CH + 2 * q + 1]);
-        const __half2 h = __floats2half2_rn(v0, v1);
+        const float v0 = __uint_as_float(r[2 * q]) + a.cpar[STAGE][16 * CH + 2 * q];
+        const float v1 = __uint_as_float(r[2 * q + 1]) + a.cpar[STAGE][16 * CH + 2 * q + 1];
+        __half2 h = __floats2half2_rn(v0, v1);
+        h = __hmax2(h, *reinterpret_cast<const __half2 *>(&a.clo[STAGE][8 * CH + q]));
+        if (a.has_hi[STAGE]) h = __hmin2(h, *reinterpret_cast<const __half2 *>(&a.chi[STAGE][8 * CH + q]));
         o[q] = keep ? *reinterpret_cast<const uint32_t *>(&h) : 0u;
     }
     lo = make_uint4(o[0], o[1], o[2], o[3]);
@@ -183,16 +191,32 @@ __device__ __forceinline__ uint4 add_h8(const uint4 &v, const uint4 &u) {
     return r4;
 }
 
+// fp16x8 max (MaxPooling2D on fp16 maps: exact)
+__device__ __forceinline__ uint4 max_h8(const uint4 &v, const uint4 &u) {
+    const __half2 *pa = reinterpret_cast<const __half2 *>(&v);
+    const __half2 *pb = reinterpret_cast<const __half2 *>(&u);
+    uint4 r4;
+    __half2 *ro = reinterpret_cast<__half2 *>(&r4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ro[e] = __hmax2(pa[e], pb[e]);
+    return r4;
+}
+
 }  // namespace
 
-__global__ void __launch_bounds__(kBtThreads, 1)
+template <int kBtEpiWarps, int kBtLoadWarps>
+__global__ void __launch_bounds__(bt_threads(kBtEpiWarps, kBtLoadWarps), kBtEpiWarps == 16 ? 1 : 2)
 block_tc_kernel(const __grid_constant__ BtArgs a) {
+    constexpr int kBtEpiGroups = kBtEpiWarps / 4;
+    constexpr int kBtThreads = bt_threads(kBtEpiWarps, kBtLoadWarps);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A0 = smem + a.a0_off, *A1 = smem + a.a1_off, *A2 = smem + a.a2_off, *OT = smem + a.o_off;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.bar_off);
-    uint64_t *ld_full = bars, *ld_empty = bars + 1, *e1_done = bars + 2, *e2_done = bars + 3, *e3_done = bars + 4, *tma_full = bars + 5;
-    uint64_t *o_free = bars + 6;
-    uint64_t *acc1_full = bars + 7, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
+    // ld_full / ld_empty / tma_full exist per loader buffer: the chain of three has ONE loader buffer (A0), the chain of
+    // two loads straight into the double-buffered A1
+    uint64_t *ld_full = bars, *ld_empty = bars + 2, *tma_full = bars + 4, *e1_done = bars + 6, *e2_done = bars + 7, *e3_done = bars + 8;
+    uint64_t *o_free = bars + 9;
+    uint64_t *acc1_full = bars + 10, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kBtNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,13 +224,14 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
-        mbar_init(ld_full, kBtLoadWarps); mbar_init(ld_empty, 1); mbar_init(tma_full, 1); mbar_init(o_free, 1);
+        for (int j = 0; j < 2; ++j) { mbar_init(&ld_full[j], kBtLoadWarps); mbar_init(&ld_empty[j], 1); mbar_init(&tma_full[j], 1); }
+        mbar_init(o_free, 1 + (a.out_pool ? kBtLoadWarps : 0));      // store warp (+ the loader warps that pool the tile)
         mbar_init(e1_done, kBtEpiWarps); mbar_init(e2_done, kBtEpiWarps); mbar_init(e3_done, kBtEpiWarps);
         for (int b = 0; b < kBtMaxBlocks; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc2_full[b], 1); mbar_init(&acc3_full[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kBtEpiWarps) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {   // resident weights + parameters; operand buffers start zeroed (positions no loader / epilogue writes)
@@ -238,82 +263,93 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         // =====================================================================================
         const int q = warp & 3, g = warp >> 2;
         const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
-        for (long long i = 0; i <= n_my; ++i) {
-            int n = 0, y0 = 0, x0 = 0;
-            // ---- E1(i): S1 accumulators -> ReLU + BN, zero outside the image -> A1 (haloed flat layout)
-            if (a.has_s1 && i < n_my) {
-                tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
-                const uint32_t par_ = (uint32_t)(i & 1);
-                if (warp == 0) BT_TL(0, i, 0);
-                with_nch(a.s1.n, [&](auto nch) {
-                    for (int b = g; b < a.s1.nb; b += kBtEpiGroups) {
-                        mbar_wait(&acc1_full[b], par_);
-                        __syncwarp();
-                        tc_fence_after();
-                        const int m = b * 128 + q * 32 + lane;
-                        const int r = (int)__umulhi((unsigned)m, a.pitch_magic), c = m - r * a.pitch;
-                        const int y = y0 - 1 + r, x = x0 - 1 + c;
-                        const bool inside = r < a.Th + 2 && y >= 0 && y < a.H && x >= 0 && x < a.W;
-                        epi_block<0, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.n), inside, true,
-                                                                 A1 + (size_t)m * 16, (size_t)a.Pn1 * 16);
-                    }
-                });
-                // warps without a block of their own still pace themselves on the stage (a free-running warp would
-                // arrive on e1_done for FUTURE tiles and corrupt the phase counts)
-                mbar_wait(&acc1_full[a.s1.nb - 1], par_);
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(e1_done);
-                if (warp == 0) BT_TL(0, i, 1);
+        // ---- E1(j): S1 accumulators -> ReLU + BN, zero outside the image -> A1[j & 1] (haloed flat layout)
+        auto E1 = [&](long long j) {
+            int n, y0, x0;
+            tile_coords(a, (long long)blockIdx.x + j * gridDim.x, n, y0, x0);
+            const uint32_t par_ = (uint32_t)(j & 1);
+            uint8_t *A1j = A1 + (size_t)(j & 1) * a.a1_stride;
+            if (warp == 0) BT_TL(0, j, 0);
+            with_nch(a.s1.n, [&](auto nch) {
+                for (int b = g; b < a.s1.nb; b += kBtEpiGroups) {
+                    mbar_wait(&acc1_full[b], par_);
+                    __syncwarp();
+                    tc_fence_after();
+                    const int m = b * 128 + q * 32 + lane;
+                    const int r = (int)__umulhi((unsigned)m, a.pitch_magic), c = m - r * a.pitch;
+                    const int y = y0 - 1 + r, x = x0 - 1 + c;
+                    const bool inside = r < a.Th + 2 && y >= 0 && y < a.H && x >= 0 && x < a.W;
+                    epi_block<0, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.n), inside, true,
+                                                             A1j + (size_t)m * 16, (size_t)a.Pn1 * 16);
+                }
+            });
+            // warps without a block of their own still pace themselves on the stage (a free-running warp would
+            // arrive on e1_done for FUTURE tiles and corrupt the phase counts)
+            mbar_wait(&acc1_full[a.s1.nb - 1], par_);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e1_done);
+            if (warp == 0) BT_TL(0, j, 1);
+        };
+        // ---- E2(j): S2 accumulators -> ReLU -> A2 (flat layout, every row written)
+        auto E2 = [&](long long j) {
+            const uint32_t par_ = (uint32_t)(j & 1);
+            if (warp == 0) BT_TL(0, j, 2);
+            with_nch(a.s2.n, [&](auto nch) {
+                for (int b = g; b < a.s2.nb; b += kBtEpiGroups) {
+                    mbar_wait(&acc2_full[b], par_);
+                    if (warp == 0 && b == g) BT_TL(0, j, 3);
+                    __syncwarp();
+                    tc_fence_after();
+                    const int m = b * 128 + q * 32 + lane;
+                    epi_block<1, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n), true, true,
+                                                             A2 + (size_t)m * 16, (size_t)a.Pn2 * 16);
+                }
+            });
+            mbar_wait(&acc2_full[a.s2.nb - 1], par_);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e2_done);
+            if (warp == 0) BT_TL(0, j, 4);
+        };
+        // ---- E3(j): S3 accumulators -> ReLU + BN -> output tile in shared memory ([Th][Tw][C] dense); the store
+        //      warp ships it with row-wise bulk copies, so no epilogue warp ever waits on a global store
+        auto E3 = [&](long long j) {
+            const uint32_t par_ = (uint32_t)(j & 1);
+            if (warp == 0) BT_TL(0, j, 5);
+            if (j >= 1) mbar_wait(o_free, (uint32_t)((j - 1) & 1));          // tile j-1 has left the staging tile
+            with_nch(a.s3.n, [&](auto nch) {
+                for (int b = g; b < a.s3.nb; b += kBtEpiGroups) {
+                    mbar_wait(&acc3_full[b], par_);
+                    if (warp == 0 && b == g) BT_TL(0, j, 6);
+                    __syncwarp();
+                    tc_fence_after();
+                    const int m = b * 128 + q * 32 + lane;
+                    const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
+                    const bool valid = ro < a.Th && co < a.Tw;
+                    epi_block<2, decltype(nch)::value, false>(a, tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, valid,
+                                                              OT + ((size_t)(ro * a.Tw + co) * a.s3.n) * 2, 0);
+                }
+            });
+            mbar_wait(&acc3_full[a.s3.nb - 1], par_);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e3_done);
+            if (warp == 0) BT_TL(0, j, 7);
+        };
+        // Schedule (see the MMA warp): while S2(i) runs, E1(i+1) fills the OTHER A1 buffer and E3(i-1) drains R3; E2(i)
+        // follows S2(i) block by block.
+        if (n_my > 0) {
+            if (a.has_s1) E1(0);
+            for (long long i = 0; i < n_my; ++i) {
+                if (a.has_s1 && i + 1 < n_my) E1(i + 1);
+                if (i >= 1) E3(i - 1);
+                E2(i);
             }
-            // ---- E3(i-1): S3 accumulators -> ReLU + BN -> output tile in shared memory ([Th][Tw][C] dense); the store
-            //      warp ships it with row-wise bulk copies, so no epilogue warp ever waits on a global store
-            if (i >= 1) {
-                const uint32_t par_ = (uint32_t)((i - 1) & 1);
-                if (warp == 0) BT_TL(0, i, 2);
-                if (i >= 2) mbar_wait(o_free, (uint32_t)(i & 1));          // tile i-2 has left the staging tile
-                with_nch(a.s3.n, [&](auto nch) {
-                    for (int b = g; b < a.s3.nb; b += kBtEpiGroups) {
-                        mbar_wait(&acc3_full[b], par_);
-                        if (warp == 0 && b == g) BT_TL(0, i, 3);
-                        __syncwarp();
-                        tc_fence_after();
-                        const int m = b * 128 + q * 32 + lane;
-                        const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
-                        const bool valid = ro < a.Th && co < a.Tw;
-                        epi_block<2, decltype(nch)::value, false>(a, tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, valid,
-                                                                  OT + ((size_t)(ro * a.Tw + co) * a.s3.n) * 2, 0);
-                    }
-                });
-                mbar_wait(&acc3_full[a.s3.nb - 1], par_);
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(e3_done);
-                if (warp == 0) BT_TL(0, i, 4);
-            }
-            // ---- E2(i): S2 accumulators -> ReLU -> A2 (flat layout, every row written)
-            if (i < n_my) {
-                const uint32_t par_ = (uint32_t)(i & 1);
-                with_nch(a.s2.n, [&](auto nch) {
-                    for (int b = g; b < a.s2.nb; b += kBtEpiGroups) {
-                        mbar_wait(&acc2_full[b], par_);
-                        if (warp == 0 && b == g) BT_TL(0, i, 5);
-                        __syncwarp();
-                        tc_fence_after();
-                        const int m = b * 128 + q * 32 + lane;
-                        epi_block<1, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n), true, true,
-                                                                 A2 + (size_t)m * 16, (size_t)a.Pn2 * 16);
-                    }
-                });
-                mbar_wait(&acc2_full[a.s2.nb - 1], par_);
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(e2_done);
-                if (warp == 0) BT_TL(0, i, 6);
-            }
+            E3(n_my - 1);
         }
     } else if (warp == kBtEpiWarps) {
         // =====================================================================================
@@ -394,52 +430,70 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 with_ks(S1.ksteps, [&](auto ks) {
                     for (uint32_t b = 0; b < S1.nb; ++b) { block_1x1(ks, S1, b); tc_commit(&acc1_full[b]); }
                 });
-                tc_commit(ld_empty);
+                tc_commit(&ld_empty[0]);
             }
             __syncwarp();
         };
-        if (a.has_s1 && n_my > 0) {
-            mbar_wait(ld_full, 0);
-            tc_fence_after();
-            issue_s1();
-        }
-        for (long long i = 0; i < n_my; ++i) {
-            const uint32_t par_ = (uint32_t)(i & 1);
-            // S2(i): its operand is A1 -- written by E1(i) (chain of three) or by the loaders (chain of two).
-            // R2 is free: e2_done(i-1) was waited for below.
-            BT_TL(1, i, 0);
-            mbar_wait(a.has_s1 ? e1_done : ld_full, par_);
-            tc_fence_after();
-            BT_TL(1, i, 1);
-            if (elect_one()) {
-                with_ks(S2.ksteps, [&](auto ks) {
-                    for (uint32_t b = 0; b < S2.nb; ++b) { block_3x3(ks, S2, b); tc_commit(&acc2_full[b]); }
-                });
-                if (!a.has_s1) tc_commit(ld_empty);
-            }
-            __syncwarp();
-            BT_TL(1, i, 2);
-            // S1(i+1): R1 is free (e1_done(i) above)
-            if (a.has_s1 && i + 1 < n_my) {
-                mbar_wait(ld_full, (uint32_t)((i + 1) & 1));
-                tc_fence_after();
-                BT_TL(1, i, 3);
-                issue_s1();
-            }
-            BT_TL(1, i, 4);
-            // S3(i): A2 complete and R2 drained (e2_done(i)); R3 free once E3(i-1) has drained it
-            if (i > 0) { mbar_wait(e3_done, (uint32_t)((i - 1) & 1)); }
-            BT_TL(1, i, 5);
-            mbar_wait(e2_done, par_);
-            tc_fence_after();
-            BT_TL(1, i, 6);
+        auto issue_s3 = [&]() {
             if (elect_one()) {
                 with_ks(S3.ksteps, [&](auto ks) {
                     for (uint32_t b = 0; b < S3.nb; ++b) { block_1x1(ks, S3, b); tc_commit(&acc3_full[b]); }
                 });
             }
             __syncwarp();
-            BT_TL(1, i, 7);
+        };
+        // Issue order per iteration:  S1(i+1)  S3(i-1)  S2(i).  The tensor pipe executes in order, so
+        //   * E1(i+1) (fills A1[(i+1)&1]) and E3(i-1) run while S2(i) (reads A1[i&1]) executes,
+        //   * E2(i) starts on S2(i)'s first finished block, i.e. after S3(i-1) has stopped reading the single A2,
+        //   * nothing the pipe needs next waits on an epilogue that has not been running for a whole stage already.
+        if (a.has_s1 && n_my > 0) {
+            mbar_wait(&ld_full[0], 0);
+            tc_fence_after();
+            issue_s1();
+        }
+        for (long long i = 0; i < n_my; ++i) {
+            const uint32_t par_ = (uint32_t)(i & 1);
+            BT_TL(1, i, 0);
+            if (a.has_s1) {
+                mbar_wait(e1_done, par_);                         // A1[i&1] is complete, R1 is free
+                tc_fence_after();
+                BT_TL(1, i, 1);
+                if (i + 1 < n_my) {
+                    mbar_wait(&ld_full[0], (uint32_t)((i + 1) & 1));
+                    tc_fence_after();
+                    issue_s1();
+                }
+            }
+            BT_TL(1, i, 2);
+            if (i >= 1) {                                         // S3(i-1): A2 complete and R2 drained; R3 drained by E3(i-2)
+                mbar_wait(e2_done, par_ ^ 1u);
+                if (i >= 2) mbar_wait(e3_done, par_);
+                tc_fence_after();
+                BT_TL(1, i, 3);
+                issue_s3();
+            }
+            BT_TL(1, i, 4);
+            if (!a.has_s1) {
+                mbar_wait(&ld_full[i & 1], (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+            }
+            BT_TL(1, i, 5);
+            if (elect_one()) {
+                StageRegs S2i = S2;
+                S2i.a_lo += (uint32_t)((i & 1) * a.a1_stride) >> 4;
+                with_ks(S2i.ksteps, [&](auto ks) {
+                    for (uint32_t b = 0; b < S2i.nb; ++b) { block_3x3(ks, S2i, b); tc_commit(&acc2_full[b]); }
+                });
+                if (!a.has_s1) tc_commit(&ld_empty[i & 1]);
+            }
+            __syncwarp();
+            BT_TL(1, i, 6);
+        }
+        if (n_my > 0) {
+            mbar_wait(e2_done, (uint32_t)((n_my - 1) & 1));
+            if (n_my >= 2) mbar_wait(e3_done, (uint32_t)((n_my - 2) & 1));
+            tc_fence_after();
+            issue_s3();
         }
     } else if (warp == kBtEpiWarps + 1 + kBtLoadWarps) {
         // =====================================================================================
@@ -450,7 +504,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
             mbar_wait(e3_done, (uint32_t)(i & 1));
-            if (elect_one()) {
+            if (lane == 0) {
                 const uint32_t bytes = (uint32_t)(min(a.Tw, a.W - x0) * a.s3.n * 2);
                 __half *g0 = a.out + (((long long)n * a.H + y0) * a.W + x0) * a.s3.n;
                 const int rows = min(a.Th, a.H - y0);
@@ -458,12 +512,15 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(g0 + (long long)ro * a.W * a.s3.n), "r"(smem_u32(OT) + (uint32_t)ro * row_smem), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 mbar_arrive(o_free);
             }
             __syncwarp();
         }
-        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
     } else {
         // =====================================================================================
@@ -471,16 +528,46 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         // =====================================================================================
         const int lt = tid - (kBtEpiWarps + 1) * 32;
         constexpr int NL = kBtLoadWarps * 32;
-        uint8_t *buf = a.has_s1 ? A0 : A1;
         const int Pn = a.has_s1 ? a.Pn0 : a.Pn1;
         const int npos = (a.Th + 2) * a.pitch;
         const int KC = a.ld_cp >> 3;
         const bool first = warp == kBtEpiWarps + 1;
+        // MaxPooling2D 2x2 (unet.py:18) of a finished output tile straight from the staging buffer: the next level's
+        // input leaves the SM together with the skip map (tile origin and extent are even, see fused_block_launch).
+        // The loader warps do it between two loads; each arrives on o_free next to the store warp.
+        auto pool_tile = [&](long long j) {
+            int n, y0, x0;
+            tile_coords(a, (long long)blockIdx.x + j * gridDim.x, n, y0, x0);
+            mbar_wait(e3_done, (uint32_t)(j & 1));
+            const int C8 = a.s3.n >> 3;                                   // 16-byte vectors per pixel
+            const int pw = min(a.Tw, a.W - x0) >> 1, ph = min(a.Th, a.H - y0) >> 1;
+            const int Wp = a.W >> 1;
+            const unsigned c8_magic = 0xFFFFFFFFu / (unsigned)C8 + 1u, pw_magic = 0xFFFFFFFFu / (unsigned)pw + 1u;
+            __half *p0 = a.out_pool + (((long long)n * (a.H >> 1) + (y0 >> 1)) * Wp + (x0 >> 1)) * a.s3.n;
+            const int items = ph * pw * C8;
+            for (int idx = lt; idx < items; idx += NL) {
+                const int f = (int)__umulhi((unsigned)idx, c8_magic), cv = idx - f * C8;
+                const int py = (int)__umulhi((unsigned)f, pw_magic), px = f - py * pw;
+                const uint8_t *src = OT + ((size_t)((2 * py) * a.Tw + 2 * px) * a.s3.n + cv * 8) * 2;
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(src);
+                const uint4 v1 = *reinterpret_cast<const uint4 *>(src + (size_t)a.s3.n * 2);
+                const uint4 v2 = *reinterpret_cast<const uint4 *>(src + (size_t)a.Tw * a.s3.n * 2);
+                const uint4 v3 = *reinterpret_cast<const uint4 *>(src + (size_t)(a.Tw + 1) * a.s3.n * 2);
+                *reinterpret_cast<uint4 *>(p0 + (py * Wp + px) * a.s3.n + cv * 8) = max_h8(max_h8(v0, v1), max_h8(v2, v3));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
+        };
+        const long long pool_lag = a.has_s1 ? 3 : 2;                      // the tile whose E3 runs while this load is in flight
         for (long long i = 0; i < n_my; ++i) {
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
+            // chain of three: one buffer (A0), free once S1(i-1) has read it; chain of two: A1[i & 1], free once S2(i-2) has
+            const int lb = a.has_s1 ? 0 : (int)(i & 1);
+            const uint32_t lph = a.has_s1 ? (uint32_t)(i & 1) : (uint32_t)((i >> 1) & 1);
+            uint8_t *buf = a.has_s1 ? A0 : A1 + (size_t)lb * a.a1_stride;
             if (first) BT_TL(2, i, 0);
-            if (i > 0) mbar_wait(ld_empty, (uint32_t)((i - 1) & 1));
+            if (a.has_s1 ? i >= 1 : i >= 2) mbar_wait(&ld_empty[lb], lph ^ 1u);
             if (first) BT_TL(2, i, 1);
             if (a.load_kind == 0) {
                 // image -> x/255 split into fp16 hi + lo so that the first layer keeps ~22 bits of the input and
@@ -557,78 +644,85 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             } else if (a.load_kind == 1) {
                 // the haloed tile: one TMA box per 8-channel plane, zero filled outside the image
                 if (first && elect_one()) {
-                    mbar_expect_tx(tma_full, (uint32_t)KC * 16u * (uint32_t)npos);
+                    mbar_expect_tx(&tma_full[lb], (uint32_t)KC * 16u * (uint32_t)npos);
                     const uint32_t dst = smem_u32(buf);
-                    for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, tma_full);
+                    for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, &tma_full[lb]);
                 }
                 __syncwarp();
-                mbar_wait(tma_full, (uint32_t)(i & 1));
+                mbar_wait(&tma_full[lb], lph);
             } else {
-                // skip tile -> operand planes, half-resolution tile -> staging, both as 16-byte cp.async (zero fill outside
-                // the maps; every item of the tile in flight at once), then nearest-upsample-2x + add in place (unet.py:32-33)
-                const int yl0 = (y0 - 1) >> 1, xl0 = (x0 - 1) >> 1;
-                const __half *in_n = reinterpret_cast<const __half *>(a.in) + (long long)n * a.H * a.W * a.ld_cp;
+                // up2x(lo) + skip (unet.py:32-33).  The haloed skip tile arrives like an ENC tile: one TMA box per
+                // 8-channel plane straight into the operand layout (zero filled outside the image).  While it is in
+                // flight every loader thread fetches its share of the half-resolution tile into registers (an item is
+                // one 16-byte (row, column, plane) vector, plane fastest: coalesced); once the boxes have landed each
+                // vector is added in place to the (up to) four positions it covers.
+                if (first && elect_one()) {
+                    mbar_expect_tx(&tma_full[0], (uint32_t)KC * 16u * (uint32_t)npos);
+                    const uint32_t dst = smem_u32(buf);
+                    for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, &tma_full[0]);
+                }
+                __syncwarp();
                 const __half *lo_n = a.in_lo + (long long)n * (a.H >> 1) * (a.W >> 1) * a.ld_cp;
-                const uint32_t dst0 = smem_u32(buf), dlo0 = smem_u32(smem + a.lo_off);
-                const int rows = a.Th + 2, Hl = a.H >> 1, Wl = a.W >> 1;
-                // a thread owns a (column, 8-channel plane) pair and walks down the rows: one predicate and one
-                // pointer increment per 16-byte item instead of a division chain
-                for (int cc = lt; cc < a.pitch * KC; cc += NL) {
-                    const int c = cc / KC, kc = cc - c * KC;                 // plane fastest: a pixel's planes are contiguous in global memory
-                    const int x = x0 - 1 + c;
-                    const bool col_ok = x >= 0 && x < a.W;
-                    const __half *src = in_n + ((long long)(y0 - 1) * a.W + x) * a.ld_cp + kc * 8;
-                    uint32_t dst = dst0 + (uint32_t)(kc * Pn + c) * 16u;
-                    for (int r = 0; r < rows; ++r, src += (long long)a.W * a.ld_cp, dst += (uint32_t)a.pitch * 16u) {
-                        const int y = y0 - 1 + r;
-                        const bool inside = col_ok && y >= 0 && y < a.H;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(inside ? src : in_n), "r"(inside ? 16 : 0) : "memory");
+                const int Hl = a.H >> 1, Wl = a.W >> 1;
+                const int yl0 = (y0 - 1) >> 1, xl0 = (x0 - 1) >> 1;               // arithmetic shifts: -1 -> -1
+                const int pl = (a.Tw >> 1) + 2, rl = (a.Th >> 1) + 2;             // half-resolution columns / rows under the haloed tile
+                const int n_items = rl * pl * KC;
+                const unsigned kc_magic = 0xFFFFFFFFu / (unsigned)KC + 1u, pl_magic = 0xFFFFFFFFu / (unsigned)pl + 1u;
+                constexpr int PB = 4;
+                bool landed = false;
+                for (int i0 = lt; i0 < n_items; i0 += PB * NL) {
+                    uint4 lv[PB];
+                    int pos[PB];                                              // kc << 20 | (r << 10) | c of the item, -1: nothing to add
+#pragma unroll
+                    for (int k = 0; k < PB; ++k) {
+                        const int idx = i0 + k * NL;
+                        const int f = (int)__umulhi((unsigned)idx, kc_magic), kc = idx - f * KC;
+                        const int r = (int)__umulhi((unsigned)f, pl_magic), c = f - r * pl;
+                        const int yl = yl0 + r, xl = xl0 + c;
+                        const bool ok = idx < n_items && yl >= 0 && yl < Hl && xl >= 0 && xl < Wl;
+                        pos[k] = ok ? ((kc << 20) | (r << 10) | c) : -1;
+                        lv[k] = make_uint4(0, 0, 0, 0);
+                        if (ok) lv[k] = *reinterpret_cast<const uint4 *>(lo_n + ((long long)yl * Wl + xl) * a.ld_cp + kc * 8);
+                    }
+                    if (!landed) { mbar_wait(&tma_full[0], (uint32_t)(i & 1)); landed = true; }
+#pragma unroll
+                    for (int k = 0; k < PB; ++k) {
+                        if (pos[k] < 0) continue;
+                        const int kc = pos[k] >> 20, r = (pos[k] >> 10) & 1023, c = pos[k] & 1023;
+                        // rows / columns of the haloed tile covered by this half-resolution pixel
+                        const int rr0 = 2 * (yl0 + r) - (y0 - 1), cc0 = 2 * (xl0 + c) - (x0 - 1);
+                        uint8_t *base = buf + ((size_t)kc * Pn) * 16;
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy) {
+                            const int rr = rr0 + dy;
+                            if (rr < 0 || rr >= a.Th + 2) continue;
+#pragma unroll
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const int cc = cc0 + dx;
+                                if (cc < 0 || cc >= a.pitch) continue;
+                                uint4 *q = reinterpret_cast<uint4 *>(base + (size_t)(rr * a.pitch + cc) * 16);
+                                *q = add_h8(*q, lv[k]);
+                            }
+                        }
                     }
                 }
-                for (int cc = lt; cc < a.pl_box * KC; cc += NL) {
-                    const int c = cc / KC, kc = cc - c * KC;
-                    const int x = xl0 + c;
-                    const bool col_ok = x >= 0 && x < Wl;
-                    const __half *src = lo_n + ((long long)yl0 * Wl + x) * a.ld_cp + kc * 8;
-                    uint32_t dst = dlo0 + (uint32_t)(kc * a.Pl + c) * 16u;
-                    for (int r = 0; r < a.rl_box; ++r, src += (long long)Wl * a.ld_cp, dst += (uint32_t)a.pl_box * 16u) {
-                        const int y = yl0 + r;
-                        const bool inside = col_ok && y >= 0 && y < Hl;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(inside ? src : lo_n), "r"(inside ? 16 : 0) : "memory");
-                    }
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                if (first) BT_TL(2, i, 3);
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                if (first) BT_TL(2, i, 4);
-                asm volatile("bar.sync 1, %0;" :: "n"(kBtLoadWarps * 32) : "memory");      // every loader's copies have landed
-                if (first) BT_TL(2, i, 5);
-                // in-place add: a thread owns a (plane, column) pair (column fastest: conflict-free shared-memory accesses);
-                // one half-resolution value serves two consecutive rows
-                const uint8_t *lo_s = smem + a.lo_off;
-                for (int cc = lt; cc < a.pitch * KC; cc += NL) {
-                    const int kc = cc / a.pitch, c = cc - kc * a.pitch;
-                    const int xl = ((x0 - 1 + c) >> 1) - xl0;
-                    uint4 *p = reinterpret_cast<uint4 *>(buf + ((size_t)kc * Pn + c) * 16);
-                    const uint4 *ql = reinterpret_cast<const uint4 *>(lo_s + ((size_t)kc * a.Pl + xl) * 16);
-                    for (int r = 0; r < rows; ++r, p += a.pitch) {
-                        const int yl = ((y0 - 1 + r) >> 1) - yl0;
-                        *p = add_h8(*p, ql[yl * a.pl_box]);
-                    }
-                }
+                if (!landed) mbar_wait(&tma_full[0], (uint32_t)(i & 1));
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(ld_full);
+            if (lane == 0) mbar_arrive(&ld_full[lb]);
             if (first) BT_TL(2, i, 2);
+            if (a.out_pool && i >= pool_lag) pool_tile(i - pool_lag);
         }
+        if (a.out_pool)
+            for (long long j = n_my > pool_lag ? n_my - pool_lag : 0; j < n_my; ++j) pool_tile(j);
     }
     // ---- teardown ----------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
     if (warp == kBtEpiWarps) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(a.tmem_cols) : "memory");
     }
 }
 
@@ -663,20 +757,29 @@ static void pack_front_b(std::vector<__half> &dst, const float *w /*[c][cout]*/,
         }
 }
 
-// BN scale folded into the weights (see BtArgs::cpar): returns the scaled HWIO kernel and fills cpar[stage]
-static std::vector<float> fold_stage(const ConvHost &L, int n, float (&cpar)[3][64]) {
+// BN scale folded into the weights (see BtArgs::cpar): returns the scaled HWIO kernel and fills the stage's epilogue constants
+static uint32_t pack_h2(float x, float y) {
+    const __half2 h = __floats2half2_rn(x, y);
+    uint32_t u;
+    memcpy(&u, &h, 4);
+    return u;
+}
+static std::vector<float> fold_stage(const ConvHost &L, BtArgs &a, int si) {
     const int taps = L.ks * L.ks;
     std::vector<float> w(L.hwio, L.hwio + (size_t)taps * L.cin * L.cout);
     const float inf = INFINITY;
-    for (int co = 0; co < 64; ++co) { cpar[0][co] = 0.f; cpar[1][co] = 0.f; cpar[2][co] = inf; }     // padding channels stay 0
+    float lo[64], hi[64];
+    for (int co = 0; co < 64; ++co) { a.cpar[si][co] = 0.f; lo[co] = 0.f; hi[co] = inf; }               // padding channels stay 0
+    a.has_hi[si] = 0;
     for (int co = 0; co < L.cout; ++co) {
         const float sc = L.bn_scale ? L.bn_scale[co] : 1.f, sh = L.bn_shift ? L.bn_shift[co] : 0.f;
         for (size_t i = co; i < w.size(); i += L.cout) w[i] *= sc;
-        cpar[0][co] = sc * L.bias[co] + sh;
-        cpar[1][co] = sc > 0.f ? sh : (sc < 0.f ? -inf : sh);
-        cpar[2][co] = sc > 0.f ? inf : sh;
+        a.cpar[si][co] = sc * L.bias[co] + sh;
+        lo[co] = sc > 0.f ? sh : (sc < 0.f ? -inf : sh);
+        hi[co] = sc > 0.f ? inf : sh;
+        if (!(sc > 0.f)) a.has_hi[si] = 1;
     }
-    (void)n;
+    for (int c2 = 0; c2 < 32; ++c2) { a.clo[si][c2] = pack_h2(lo[2 * c2], lo[2 * c2 + 1]); a.chi[si][c2] = pack_h2(hi[2 * c2], hi[2 * c2 + 1]); }
     return w;
 }
 
@@ -685,81 +788,97 @@ static bool bt_disabled() {
     return v && v[0] && v[0] != '0';
 }
 
-// Chooses the tile and lays out shared memory / TMEM.  Returns false when the block does not fit
-// (weights too large to stay resident, or no tile satisfies the 512-column TMEM budget).
 static inline int round8(int v) { return (v + 7) / 8 * 8; }
 
-struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, pl_box, rl_box, Pl; size_t bytes; };
+struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, cols; size_t bytes; };
 
 // shared-memory / TMEM footprint of a candidate tile; plane strides are multiples of 8 positions so that every
 // plane starts 128-byte aligned (TMA destination)
-static bool bt_geom(const FusedBlock &fb, int th, int tw, BtGeom &g) {
+static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t smem_max, BtGeom &g) {
     const BtArgs &a = fb.args;
     const int pitch = tw + 2;
     const int n1 = a.has_s1 ? a.s1.n : 0, n2 = a.s2.n, n3 = a.s3.n;
     g.nb1 = a.has_s1 ? ((th + 2) * pitch + 127) / 128 : 0;
     g.nb2 = (th * pitch + 127) / 128;
     if (g.nb1 > kBtMaxBlocks || g.nb2 > kBtMaxBlocks) return false;
-    if (g.nb1 * n1 + g.nb2 * n2 + g.nb2 * n3 > 512) return false;
-    g.pl_box = (tw + 1) / 2 + 2; g.rl_box = th / 2 + 2;
-    if (pitch > 256 || g.pl_box > 256) return false;                 // TMA box limits
+    g.cols = g.nb1 * n1 + g.nb2 * n2 + g.nb2 * n3;
+    if (g.cols > cols_max) return false;
+    if (pitch > 256 || th + 2 > 256) return false;                   // TMA box limits
     g.Pn0 = round8(g.nb1 * 128);
     g.Pn1 = round8(std::max(std::max(g.nb1 * 128, g.nb2 * 128 + 2 * pitch + 2), (th + 2) * pitch));
     g.Pn2 = round8(g.nb2 * 128);
-    g.Pl = round8(g.pl_box * g.rl_box);
     size_t off = (size_t)fb.w_bytes + (size_t)fb.par_floats * 4;
     off = (off + 127) / 128 * 128;
     if (a.has_s1) off += (size_t)g.Pn0 * (a.s1.ksteps * 2) * 16;
-    off += (size_t)g.Pn1 * (a.s2.ksteps * 2) * 16;
+    off += 2 * (((size_t)g.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128);     // A1 is double-buffered
     off += (size_t)g.Pn2 * (a.s3.ksteps * 2) * 16;
-    if (a.load_kind == 2) off += (size_t)g.Pl * (a.ld_cp / 8) * 16;
     off += ((size_t)th * tw * n3 * 2 + 127) / 128 * 128;
     if (a.load_kind == 0) off += 1024;
     off += (size_t)kBtNumBars * 8 + 16;
     g.bytes = off;
-    return off <= (size_t)kBtSmemMax;
+    return off <= smem_max;
 }
 
-// Chooses the tile and lays out shared memory / TMEM.  Returns false when the block does not fit
-// (weights too large to stay resident, or no tile satisfies the 512-column TMEM budget).
+// Cheapest tile for a TMEM / shared-memory budget.  Cost = tcgen05.mma instructions per image (every small-N MMA
+// costs about the same: its 4 KB A operand read) plus a fixed per-tile term for the hand-offs (measured: a tile costs a few thousand cycles of
+// pipeline latency whatever its size, so fewer, larger tiles win); partial
+// edge tiles are charged in full.  Tiles are even-sized so that the store warp can carry the 2x2 max-pool.
+static double bt_best_tile(const FusedBlock &fb, int H, int W, int cols_max, size_t smem_max, int &bTh, int &bTw) {
+    const BtArgs &a = fb.args;
+    double best = -1.0;
+    BtGeom g{};
+    for (int th = 2; th <= 16; th += 2) {
+        if (th > H + 1) break;
+        for (int tw = 8; tw <= 254; tw += 2) {
+            if (tw > W + 1 && tw > 8) break;
+            if (!bt_geom(fb, th, tw, cols_max, smem_max, g)) continue;
+            const double tiles = (double)((W + tw - 1) / tw) * ((H + th - 1) / th);
+            const double per_tile = (a.has_s1 ? g.nb1 * a.s1.ksteps : 0) + g.nb2 * (9.0 * a.s2.ksteps + a.s3.ksteps) + 60.0;
+            const double cost = tiles * per_tile;
+            if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && th * tw > bTh * bTw)) { best = cost; bTh = th; bTw = tw; }
+        }
+    }
+    return best;
+}
+
+// Chooses the launch shape (1 or 2 CTAs per SM) and the tile, lays out shared memory / TMEM.  Returns false when
+// the block does not fit (weights too large to stay resident, or no tile satisfies the TMEM budget).
 static bool bt_plan(FusedBlock &fb, int H, int W) {
     BtArgs &a = fb.args;
     a.H = H; a.W = W;
-    double best = -1.0;
-    int bTh = 0, bTw = 0;
-    const int th_opts[] = {8, 6, 4, 2};
+    int th1 = 0, tw1 = 0, th2 = 0, tw2 = 0;
+    const double c1 = bt_best_tile(fb, H, W, 512, kBtSmemMax, th1, tw1);
+    const double c2 = bt_best_tile(fb, H, W, 256, kBtSmemMax2, th2, tw2);
+    int force = 0;
+    if (const char *v = getenv("IMK_BT_CTAS"); v && v[0]) force = atoi(v);
+    // measured (HeLa, r01): two co-resident half-size pipelines do not beat one full-size pipeline (the epilogue warps of
+    // both CTAs share the same issue slots), so the 2-CTA shape is used only when nothing fits the 1-CTA budget
+    bool two = c2 > 0 && c1 < 0;
+    if (force == 1 && c1 > 0) two = false;
+    if (force == 2 && c2 > 0) two = true;
+    if (!two && c1 < 0) return false;
+    fb.ctas_per_sm = two ? 2 : 1;
+    const int bTh = two ? th2 : th1, bTw = two ? tw2 : tw1;
     BtGeom g{};
-    for (int th : th_opts) {
-        for (int split = 1; split <= 16; split *= 2) {
-            const int tw = (W + split - 1) / split;
-            if (tw < 8 && split > 1) break;
-            if (!bt_geom(fb, th, tw, g)) continue;
-            const int th_eff = std::min(th, H), tw_eff = std::min(tw, W);
-            // useful fraction of the haloed work, with a mild preference for larger tiles (fewer hand-offs)
-            const double eff = (double)(th_eff * tw_eff) / ((th + 2.0) * (tw + 2.0)) + 1e-3 * th * tw / (8.0 * 256.0);
-            if (eff > best) { best = eff; bTh = th; bTw = tw; }
-        }
-    }
-    if (best < 0) return false;
-    bt_geom(fb, bTh, bTw, g);
+    bt_geom(fb, bTh, bTw, two ? 256 : 512, two ? kBtSmemMax2 : kBtSmemMax, g);
     a.Th = bTh; a.Tw = bTw; a.pitch = bTw + 2;
     a.pitch_magic = (unsigned)((0x100000000ull + a.pitch - 1) / a.pitch);
     a.tiles_x = (W + bTw - 1) / bTw; a.tiles_y = (H + bTh - 1) / bTh;
     a.s1.nb = g.nb1; a.s2.nb = a.s3.nb = g.nb2;
     a.s1.col = 0; a.s2.col = g.nb1 * (a.has_s1 ? a.s1.n : 0); a.s3.col = a.s2.col + g.nb2 * a.s2.n;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < g.cols) a.tmem_cols *= 2;
     a.Pn0 = g.Pn0; a.Pn1 = g.Pn1; a.Pn2 = g.Pn2;
-    a.pl_box = g.pl_box; a.rl_box = g.rl_box; a.Pl = g.Pl;
     size_t off = (size_t)fb.w_bytes;
     a.par_off_b = (int)off; off += (size_t)fb.par_floats * 4; off = (off + 127) / 128 * 128;
     a.a0_off = (int)off; if (a.has_s1) off += (size_t)a.Pn0 * (a.s1.ksteps * 2) * 16;
-    a.a1_off = (int)off; off += (size_t)a.Pn1 * (a.s2.ksteps * 2) * 16;
+    a.a1_off = (int)off; a.a1_stride = (int)(((size_t)a.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128); off += 2 * (size_t)a.a1_stride;
     a.a2_off = (int)off; off += (size_t)a.Pn2 * (a.s3.ksteps * 2) * 16;
-    a.lo_off = (int)off; if (a.load_kind == 2) off += (size_t)a.Pl * (a.ld_cp / 8) * 16;
     a.o_off = (int)off; off += ((size_t)a.Th * a.Tw * a.s3.n * 2 + 127) / 128 * 128;
     a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
     a.bar_off = (int)off; off += (size_t)kBtNumBars * 8 + 16;        // everything in [a0_off, bar_off) starts zeroed
     fb.smem = off;
-    return off <= (size_t)kBtSmemMax;
+    return off <= (size_t)(two ? kBtSmemMax2 : kBtSmemMax);
 }
 
 // ---- TMA tensor maps (driver entry point fetched through the runtime: no -lcuda) ---------------------
@@ -817,7 +936,7 @@ int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W,
         s.taps = front ? 1 : c.ks * c.ks; s.ksteps = cin_p / 16; s.n = n;
         s.w_off = (int)(w.size() * sizeof(__half));
         const int si = &s == &a.s1 ? 0 : (&s == &a.s2 ? 1 : 2);
-        const std::vector<float> ws = fold_stage(c, n, a.cpar[si]);
+        const std::vector<float> ws = fold_stage(c, a, si);
         if (front) pack_front_b(w, ws.data(), c.cin, c.cout, n); else pack_umma_b(w, ws.data(), c.ks, c.cin, c.cout, cin_p, n);
         s.par_off = 0;
     };
@@ -844,27 +963,35 @@ int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W,
     if (rc) return rc;
     fb.ok = true;
     if (const char *v = getenv("IMK_BT_VERBOSE"); v && v[0] == '1')
-        fprintf(stderr, "[imk] fused block kind=%d %dx%d: tile %dx%d, M blocks %d/%d, TMEM %d cols, smem %zu B, weights %d B\n", kind, H, W,
-                a.Th, a.Tw, a.s1.nb, a.s2.nb, a.s3.col + a.s3.nb * a.s3.n, fb.smem, fb.w_bytes);
+        fprintf(stderr, "[imk] fused block kind=%d %dx%d: %d CTA/SM, tile %dx%d, M blocks %d/%d, TMEM %d cols, smem %zu B, weights %d B\n", kind, H, W,
+                fb.ctas_per_sm, a.Th, a.Tw, a.s1.nb, a.s2.nb, a.s3.col + a.s3.nb * a.s3.n, fb.smem, fb.w_bytes);
     return IMK_OK;
 }
 
-int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo, __half *out, int64_t n, int swap_rb,
-                       int in_f32, cudaStream_t stream) {
+bool fused_block_can_pool(const FusedBlock &fb) {
+    const BtArgs &a = fb.args;
+    return fb.ok && a.Th % 2 == 0 && a.Tw % 2 == 0 && a.H % 2 == 0 && a.W % 2 == 0;
+}
+
+int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo, __half *out, __half *out_pool, int64_t n,
+                       int swap_rb, int in_f32, cudaStream_t stream) {
     BtArgs a = fb.args;
     a.in = in; a.in_lo = in_lo; a.out = out; a.swap_rb = swap_rb; a.in_f32 = in_f32;
+    a.out_pool = out_pool;
+    if (out_pool && !fused_block_can_pool(fb)) { set_error("fused block: the tile cannot carry the 2x2 max-pool"); return IMK_EINVAL; }
     a.n_tiles = (long long)n * a.tiles_x * a.tiles_y;
     if (a.n_tiles <= 0) return IMK_OK;
-    if (a.load_kind == 1) {
+    if (a.load_kind != 0) {
         int rc = make_map(&a.tm_in, in, n, a.H, a.W, a.ld_cp, a.pitch, a.Th + 2);
         if (rc) return rc;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        IMK_CUDA(cudaFuncSetAttribute(block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmemMax));
+        IMK_CUDA(cudaFuncSetAttribute(block_tc_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmemMax));
+        IMK_CUDA(cudaFuncSetAttribute(block_tc_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmemMax2));
         attr_set = true;
     }
-    const int grid = (int)std::min<long long>(a.n_tiles, kNumSMs);
+    const int grid = (int)std::min<long long>(a.n_tiles, (long long)kNumSMs * fb.ctas_per_sm);
     static long long *dbg_dev = nullptr;
     const char *tl = getenv("IMK_BT_TIMELINE");
     a.dbg = nullptr;
@@ -873,7 +1000,8 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
         IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 3 * 16 * 8, stream));
         a.dbg = dbg_dev;
     }
-    block_tc_kernel<<<grid, kBtThreads, fb.smem, stream>>>(a);
+    if (fb.ctas_per_sm == 2) block_tc_kernel<8, 4><<<grid, bt_threads(8, 4), fb.smem, stream>>>(a);
+    else block_tc_kernel<16, 8><<<grid, bt_threads(16, 8), fb.smem, stream>>>(a);
     IMK_LAUNCHED();
     if (a.dbg) {
         long long h[3 * 16 * 8];

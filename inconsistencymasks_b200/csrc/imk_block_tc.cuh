@@ -19,6 +19,7 @@ struct BtArgs {
     const void *in;                     // uint8 image (FRONT) or fp16 NHWC map
     const __half *in_lo;                // DEC: the half-resolution map that is upsampled and added
     __half *out;
+    __half *out_pool;                   // optional: MaxPooling2D 2x2 of `out` (fp16 NHWC at half resolution), written by the store warp
     const uint8_t *wpk;                 // packed weights of all stages (device)
     const float *par;                   // bias / BN parameters of all stages (device)
     int w_bytes, par_floats;
@@ -30,16 +31,18 @@ struct BtArgs {
     BtStage s1, s2, s3;
     int Pn0, Pn1, Pn2;
     int par_off_b, a0_off, a1_off, a2_off, bar_off; // byte offsets in dynamic shared memory
+    int a1_stride;                      // A1 is double-buffered (tile parity): bytes between the two copies
     unsigned pitch_magic;               // ceil(2^32 / pitch)
-    int lo_off, Pl, pl_box, rl_box;     // DEC: staging of the half-resolution tile ([kc][rl_box * pl_box (+pad)][8 ch])
+    int tmem_cols;                      // TMEM columns to allocate (power of two >= the three accumulator regions)
     int o_off;                          // output staging tile [Th][Tw][Cout] fp16
     int lut_off;                        // FRONT: 256-entry table of x/255 as fp16 hi | lo << 16
-    alignas(64) CUtensorMap tm_in;      // TMA maps (ENC / DEC): {8 ch, pitch, Th + 2, 1} boxes of the fp16 NHWC input ...
-    alignas(64) CUtensorMap tm_lo;      // ... and {8 ch, pl_box, rl_box, 1} boxes of the half-resolution map
+    alignas(64) CUtensorMap tm_in;      // TMA map (ENC / DEC): {8 ch, pitch, Th + 2, 1} boxes of the fp16 NHWC input / skip map
     // Epilogue constants, read as constant-bank operands (no loads): the BN scale is folded into the weights, so a
-    // stage's epilogue is  v = acc + cpar[s][0][c];  v = min(max(v, cpar[s][1][c]), cpar[s][2][c])
+    // stage's epilogue is  h = fp16(acc + cpar[s][c]);  h = min(max(h, clo[s][c]), chi[s][c])  on packed halves
     //   scale > 0: (b', lo, hi) = (scale*bias + shift, shift, +inf)   scale < 0: (.., -inf, shift)   ReLU only: (bias, 0, +inf)
-    float cpar[3][3][64];
+    float cpar[3][64];
+    uint32_t clo[3][32], chi[3][32];    // half2 pairs of the clamp bounds, rounded to fp16
+    int has_hi[3];                      // some channel of the stage has a finite upper bound (a BN scale <= 0)
     long long *dbg;                     // optional timeline buffer (IMK_BT_TIMELINE=1): [3 roles][16 tiles][8 events] clocks of CTA 0
 };
 
@@ -48,6 +51,7 @@ struct FusedBlock {                     // one fused U-Net block of one model (d
     bool ok = false;
     BtArgs args{};
     int w_bytes = 0, par_floats = 0;
+    int ctas_per_sm = 1;                // launch shape: 1 -> block_tc_kernel<16, 8>, 2 -> block_tc_kernel<8, 4>
     size_t smem = 0;
 };
 
@@ -60,7 +64,9 @@ struct ConvHost {                       // host view of one Conv2D (+BN) while i
 // kind: 0 FRONT (in 1x1, conv3, conv1 of level 0), 1 ENC (conv3, conv1), 2 DEC (conv1a, conv3, conv1b).
 // Leaves fb.ok == false (and returns IMK_OK) when the block does not fit the resident-weight design.
 int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned);
-int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo, __half *out, int64_t n, int swap_rb,
-                       int in_f32, cudaStream_t stream);
+// out_pool (optional, needs fused_block_can_pool): the 2x2 max-pooled map is written next to `out` by the same kernel.
+bool fused_block_can_pool(const FusedBlock &fb);
+int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo, __half *out, __half *out_pool, int64_t n,
+                       int swap_rb, int in_f32, cudaStream_t stream);
 
 }  // namespace imk

@@ -22,7 +22,9 @@
 // Epilogue: tcgen05.ld (32 lanes x 16 columns) -> + bias -> ReLU -> BN affine -> fp16 ->
 // 2 x 128-bit stores per 16 channels.  Optional prologue: nearest-upsample-2x + add
 // (unet.py:32-33) fused into the strip load.
+#include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 #include "imk_unet.cuh"
 
 namespace imk {
@@ -316,51 +318,67 @@ static int next_pow2_cols(int c) {
     return p;
 }
 
-// Chooses the strip height and the weight staging for a layer; returns false if nothing fits.
-static bool tc_plan(const ConvLayer &L, int h, int w, TcArgs &a) {
+// Chooses the strip height, the weight staging and the residency (1 or 2 CTAs per SM) for a layer with a small
+// cost model (cycles): a CTA loads its strip, streams the weights once while it issues units x M-blocks MMAs, and
+// drains its accumulators; a ring stage whose MMAs take less than the L2 round trip stalls on the weight stream;
+// two co-resident CTAs share the tensor pipe but hide each other's load / epilogue phases.  Returns false if
+// nothing fits.
+static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &a) {
     a.H = h; a.W = w; a.cin_p = L.cin_p; a.cout_p = L.cout_p;
     a.taps = L.ks * L.ks; a.halo = L.ks / 2; a.pitch = w + 2 * a.halo;
     a.ksteps = L.cin_p / 16;
     a.units_total = a.taps * a.ksteps;
     a.unit_bytes = L.cout_p * 32;
     const int KC = L.cin_p / 8;
+    const double mma_cyc = std::max(39.0, L.cout_p / 2.0);          // measured: tools/ubench/mma_issue.cu
+    const double l2_trip = 1500.0;
+    double best = -1.0;
     for (int stage_max = kWStageMax; stage_max >= 8 * 1024; stage_max >>= 1) {
         int U = 1;
         for (int d = 1; d <= a.units_total; ++d)
             if (a.units_total % d == 0 && d * a.unit_bytes <= stage_max) U = d;
-        a.units_per_stage = U;
-        a.stage_bytes = U * a.unit_bytes;
-        a.n_stages = a.units_total / U;
-        const int fixed = kWSlots * a.stage_bytes + 3 * L.cout_p * 4 + 128;
+        const int stage_bytes = U * a.unit_bytes, n_stages = a.units_total / U;
+        const int fixed = kWSlots * stage_bytes + 3 * L.cout_p * 4 + 128;
         for (int pass = 0; pass < 2; ++pass) {
             const int max_cols = pass == 0 ? 256 : 512;
             const int max_smem = pass == 0 ? 110 * 1024 : 220 * 1024;
-            for (int th = 16; th >= 1; th >>= 1) {
-                if (th > h && th > 1) continue;
+            const int resident = pass == 0 ? 2 : 1;
+            for (int th = std::min(h, 32); th >= 1; --th) {
                 const int nmb = (th * a.pitch + 127) / 128;
-                if (nmb * L.cout_p > max_cols) continue;
+                if (nmb > kMaxMBlocks || nmb * L.cout_p > max_cols) continue;
                 const int pn = (nmb * 128 + 2 * a.halo * a.pitch + 2 * a.halo) | 1;
                 const int act_bytes = (KC * pn * 16 + 127) / 128 * 128;
                 if (act_bytes + fixed > max_smem) continue;
-                a.Th = th; a.n_mblocks = nmb; a.Pn = pn; a.act_bytes = act_bytes;
-                a.tmem_cols = next_pow2_cols(nmb * L.cout_p);
-                return true;
+                const double ctas = (double)((h + th - 1) / th) * (double)std::max<int64_t>(n_images, 1);
+                const double t_mma = a.units_total * nmb * mma_cyc;
+                const double t_stream = n_stages > 1 ? n_stages * std::max(U * nmb * mma_cyc, l2_trip / (kWSlots - 1)) : t_mma;
+                const double t_io = 2500.0 + nmb * (L.cout_p / 16) * 120.0;
+                const double t_cta = t_io + std::max(t_mma, t_stream);
+                const double wave = resident == 2 ? std::max(2.0 * t_mma, t_cta) : t_cta;
+                const double waves = std::ceil(ctas / (double)(kNumSMs * resident));
+                const double cost = waves * wave;
+                if (best < 0 || cost < best) {
+                    best = cost;
+                    a.units_per_stage = U; a.stage_bytes = stage_bytes; a.n_stages = n_stages;
+                    a.Th = th; a.n_mblocks = nmb; a.Pn = pn; a.act_bytes = act_bytes;
+                    a.tmem_cols = next_pow2_cols(nmb * L.cout_p);
+                }
             }
         }
     }
-    return false;
+    return best >= 0;
 }
 
 bool conv_tc_fits(const ConvLayer &L, int h, int w) {
     TcArgs a{};
-    return conv_tc_supported(L) && L.w_umma && tc_plan(L, h, w, a);
+    return conv_tc_supported(L) && L.w_umma && tc_plan(L, h, w, 64, a);
 }
 
 int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __half *out, __half *pool_out,
                    int64_t n, int h, int w, cudaStream_t stream) {
     (void)pool_out;
     TcArgs a{};
-    if (!tc_plan(L, h, w, a)) { set_error("conv_tc_launch: no strip configuration fits (cin_p=%d cout_p=%d %dx%d)", L.cin_p, L.cout_p, h, w); return IMK_ESTATE; }
+    if (!tc_plan(L, h, w, n, a)) { set_error("conv_tc_launch: no strip configuration fits (cin_p=%d cout_p=%d %dx%d)", L.cin_p, L.cout_p, h, w); return IMK_ESTATE; }
     a.in = in; a.in_lo = in_lo; a.out = out; a.wpk = L.w_umma;
     a.bias = L.bias; a.bn_scale = L.has_bn ? L.bn_scale : nullptr; a.bn_shift = L.bn_shift;
     const size_t smem = (size_t)a.act_bytes + kWSlots * a.stage_bytes + 3 * a.cout_p * 4 + (2 * kWSlots + kMaxMBlocks) * 8 + 16;
@@ -369,6 +387,9 @@ int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __
         IMK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = 227 * 1024;
     }
+    if (env_flag("IMK_TC_VERBOSE"))
+        fprintf(stderr, "[imk] conv_tc %dx%d k%d %d->%d: strip %d rows, %d M blocks, TMEM %d cols, %d stages of %d B, act %d B\n", h, w, L.ks,
+                L.cin_p, L.cout_p, a.Th, a.n_mblocks, a.tmem_cols, a.n_stages, a.stage_bytes, a.act_bytes);
     dim3 grid((h + a.Th - 1) / a.Th, (unsigned)n);
     conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(a);
     IMK_LAUNCHED();

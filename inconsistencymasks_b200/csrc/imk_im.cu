@@ -229,7 +229,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 template <int C>                          // image channels at compile time (1, 3, 4; 0 = run-time)
-__global__ void __launch_bounds__(kMcThreads)
+__global__ void __launch_bounds__(kMcThreads, 3)
 im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, int K, int n_slots,
                          const uint8_t *__restrict__ img, int c, int block_in, int block_out,
                          uint8_t *__restrict__ img_out, uint8_t *__restrict__ label_out, uint8_t *__restrict__ im_out,
@@ -280,6 +280,14 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
         const int64_t n_lo = small ? (int64_t)((uint32_t)p0 / (uint32_t)HW) : p0 / HW;
         const bool uniform = (p0 + pc <= (n_lo + 1) * HW);
         const int64_t n_px = live ? (uniform ? n_lo : (small ? (int64_t)((uint32_t)(p0 + tid) / (uint32_t)HW) : (p0 + tid) / HW)) : -1;
+        // the image vector this lane will blank in the epilogue: requested before the slabs are scanned, so that
+        // its DRAM latency is covered by the argmax work instead of stalling the warp at the end of every tile
+        const int64_t wpx = p0 + warp * 32;                      // first pixel of this warp
+        const int cc = C > 0 ? C : c;
+        const int ig = lane >= cc ? 1 : 0, iv = lane - ig * cc;  // 16-pixel group, 16-byte vector inside it
+        const bool img_lane = img_out && lane < 2 * cc && wpx + 16 * ig < p0 + pc;
+        uint4 pix = make_uint4(0, 0, 0, 0);
+        if (img_lane) pix = ldg_stream(img + (wpx + 16 * ig) * cc + 16 * iv);
         uint32_t disagree = 0;
         int a0 = 0;
         for (int m = 0; m < M; ++m) {
@@ -301,7 +309,6 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
         const uint32_t im_mask = __ballot_sync(0xffffffffu, live && disagree);
         lab_s[warp * 32 + lane] = (live && !disagree) ? (uint8_t)a0 : 0;
         __syncwarp();
-        const int64_t wpx = p0 + warp * 32;                      // first pixel of this warp
         if (lane < 2 && wpx + 16 * lane < p0 + pc) {
             const int64_t px = wpx + 16 * lane;
             const uint32_t bits = im_mask >> (16 * lane);
@@ -311,18 +318,12 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
             stg_stream(label_out + px, *reinterpret_cast<const uint4 *>(lab_s + warp * 32 + 16 * lane));   // 0 where the IM is set
             stg_stream(im_out + px, make_uint4(imw[0], imw[1], imw[2], imw[3]));
         }
-        const int cc = C > 0 ? C : c;
-        if (img_out && lane < 2 * cc) {
-            const int g = lane >= cc ? 1 : 0, v = lane - g * cc;   // 16-pixel group, 16-byte vector inside it
-            const int64_t px = wpx + 16 * g;
-            if (px < p0 + pc) {
-                const uint32_t bits = block_in ? (im_mask >> (16 * g)) : 0u;
-                uint32_t imw[4];
+        if (img_lane) {
+            const uint32_t bits = block_in ? (im_mask >> (16 * ig)) : 0u;
+            uint32_t imw[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(bits4_to_bytes01(bits >> (4 * j)));
-                const uint4 pix = ldg_stream(img + px * cc + 16 * v);
-                stg_stream(img_out + px * cc + 16 * v, blank_vec_sel<C>(pix, imw, cc, v));
-            }
+            for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(bits4_to_bytes01(bits >> (4 * j)));
+            stg_stream(img_out + (wpx + 16 * ig) * cc + 16 * iv, blank_vec_sel<C>(pix, imw, cc, iv));
         }
         __syncwarp();
     }

@@ -28,8 +28,9 @@ __device__ __forceinline__ void argmax_step(float v, int k, float &best, int &ar
     if (!(best != best) && (v > best || v != v)) { best = v; arg = k; }
 }
 
+// exact rule for any input (NaN / signed zeros) through the order keys; K may be a run-time value
 template <int KT>
-__device__ __forceinline__ int argmax_row_t(const float *__restrict__ row, int K) {
+__device__ __forceinline__ int argmax_row_keys(const float *__restrict__ row, int K) {
     uint32_t best = order_key(row[0]);
     int arg = 0;
     if constexpr (KT > 0) {
@@ -46,6 +47,49 @@ __device__ __forceinline__ int argmax_row_t(const float *__restrict__ row, int K
         }
     }
     return arg;
+}
+
+// Fast path for a compile-time class count: a tree of independent merges (FSETP + FSEL + SEL each, ties keep the
+// lower index: np.argmax replaces the running maximum only when `!(v <= max)`), plus the row sum, which is NaN
+// exactly when the row holds a NaN (or both infinities).  Only such rows take the exact order-key scan, so the
+// common case costs ~4 instructions per element with K/2-way instruction-level parallelism.
+template <int LO, int N>
+__device__ __forceinline__ void argmax_tree(const float *__restrict__ row, float &best, int &arg, float &sum) {
+    if constexpr (N == 1) {
+        best = row[LO]; arg = LO; sum = best;
+    } else {
+        float bl, br, sl, sr;
+        int al, ar;
+        argmax_tree<LO, N / 2>(row, bl, al, sl);
+        argmax_tree<LO + N / 2, N - N / 2>(row, br, ar, sr);
+        const bool gt = br > bl;
+        best = gt ? br : bl; arg = gt ? ar : al; sum = sl + sr;
+    }
+}
+
+// rows wider than 8 classes are folded chunk by chunk (8-wide trees merged left to right) so that only one
+// chunk of values is live at a time
+template <int KT>
+__device__ __forceinline__ int argmax_row_t(const float *__restrict__ row, int K) {
+    if constexpr (KT > 0) {
+        constexpr int CH = 8;
+        float best, sum;
+        int arg;
+        argmax_tree<0, (KT < CH ? KT : CH)>(row, best, arg, sum);
+#pragma unroll
+        for (int k0 = CH; k0 < KT; k0 += CH) {
+            float b2, s2;
+            int a2;
+            if (k0 + CH <= KT) argmax_tree<0, CH>(row + k0, b2, a2, s2);
+            else argmax_tree<0, (KT % CH == 0 ? CH : KT % CH)>(row + k0, b2, a2, s2);
+            const bool gt = b2 > best;
+            best = gt ? b2 : best; arg = gt ? a2 + k0 : arg; sum += s2;
+        }
+        if (sum != sum) arg = argmax_row_keys<KT>(row, K);
+        return arg;
+    } else {
+        return argmax_row_keys<0>(row, K);
+    }
 }
 
 __device__ __forceinline__ int argmax_row(const float *__restrict__ row, int K) {

@@ -513,11 +513,18 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
     };
     int li = 1;
     const __half *x = nullptr;
+    // a fused block whose tile is even-sized also writes the 2x2 max-pooled map (the next level's input)
+    auto pooled_of = [&](int l) -> __half * { return (l < 3) ? lv[l + 1].b : lv[4].a; };
     if (fused && net->fb_enc[0].ok) {
-        // input block + encoder block 1 in one kernel: image -> lvl0.skip
-        IMK_PROFILE("block_front", 0, stream);
-        if ((rc = fused_block_launch(net->fb_enc[0], images, nullptr, lv[0].skip, n, d.swap_rb, in_dtype == IMK_IN_F32, stream))) return rc;
+        // input block + encoder block 1 in one kernel: image -> lvl0.skip (+ pooled)
+        const bool pf = fused_block_can_pool(net->fb_enc[0]);
+        {
+            IMK_PROFILE("block_front", 0, stream);
+            if ((rc = fused_block_launch(net->fb_enc[0], images, nullptr, lv[0].skip, pf ? pooled_of(0) : nullptr, n, d.swap_rb,
+                                         in_dtype == IMK_IN_F32, stream))) return rc;
+        }
         li = 3;
+        x = pf ? pooled_of(0) : pool(0);
     } else {
         {
             const ConvLayer &c0 = L[0];
@@ -533,26 +540,30 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
         }
         if ((rc = launch_conv(net, li++, lv[0].b, nullptr, lv[0].a, n, lv[0].h, lv[0].w, stream))) return rc;
         if ((rc = launch_conv(net, li++, lv[0].a, nullptr, lv[0].skip, n, lv[0].h, lv[0].w, stream))) return rc;
+        x = pool(0);
     }
-    x = pool(0);
     IMK_CUDA(cudaGetLastError());
     // encoder blocks 2..4: conv3 -> a ; conv1+BN -> skip ; maxpool -> next level's b
     for (int l = 1; l < 4; ++l) {
         if (fused && net->fb_enc[l].ok) {
-            IMK_PROFILE("block_enc", li, stream);
-            if ((rc = fused_block_launch(net->fb_enc[l], x, nullptr, lv[l].skip, n, 0, 0, stream))) return rc;
+            const bool pf = fused_block_can_pool(net->fb_enc[l]);
+            {
+                IMK_PROFILE("block_enc", li, stream);
+                if ((rc = fused_block_launch(net->fb_enc[l], x, nullptr, lv[l].skip, pf ? pooled_of(l) : nullptr, n, 0, 0, stream))) return rc;
+            }
             li += 2;
+            x = pf ? pooled_of(l) : pool(l);
         } else {
             if ((rc = launch_conv(net, li++, x, nullptr, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
             if ((rc = launch_conv(net, li++, lv[l].a, nullptr, lv[l].skip, n, lv[l].h, lv[l].w, stream))) return rc;
+            x = pool(l);
         }
-        x = pool(l);
         IMK_CUDA(cudaGetLastError());
     }
     // bottleneck: conv3 (128a -> 256a) -> lvl4.b ; conv1+BN (256a -> 128a) -> lvl4.skip
     if (fused && net->fb_enc[4].ok) {
         IMK_PROFILE("block_enc", li, stream);
-        if ((rc = fused_block_launch(net->fb_enc[4], x, nullptr, lv[4].skip, n, 0, 0, stream))) return rc;
+        if ((rc = fused_block_launch(net->fb_enc[4], x, nullptr, lv[4].skip, nullptr, n, 0, 0, stream))) return rc;
         li += 2;
     } else {
         if ((rc = launch_conv(net, li++, x, nullptr, lv[4].b, n, lv[4].h, lv[4].w, stream))) return rc;
@@ -563,7 +574,7 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
     for (int l = 3; l >= 0; --l) {
         if (fused && net->fb_dec[l].ok) {
             IMK_PROFILE("block_dec", li, stream);
-            if ((rc = fused_block_launch(net->fb_dec[l], lv[l].skip, x, lv[l].a, n, 0, 0, stream))) return rc;
+            if ((rc = fused_block_launch(net->fb_dec[l], lv[l].skip, x, lv[l].a, nullptr, n, 0, 0, stream))) return rc;
             li += 3;
         } else {
             if ((rc = launch_conv(net, li++, lv[l].skip, x, lv[l].a, n, lv[l].h, lv[l].w, stream))) return rc;
