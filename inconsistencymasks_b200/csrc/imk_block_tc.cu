@@ -142,32 +142,68 @@ __device__ __forceinline__ void epi16(const BtArgs &a, const uint32_t (&r)[16], 
     hi = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-// one M block of an epilogue phase: NCH chunks of 16 columns, TMEM -> constants -> fp16 -> dst planes / pixel-major tile
+// Epilogue work is done in PAIRS of 16-column units: both tcgen05.ld are in flight before the one wait, so the TMEM
+// read latency is exposed once per 32 columns instead of once per 16.  A unit is (M block, chunk of 16 channels):
 //   PLANES: dst is an operand buffer, chunk c lands at plane 2c / 2c+1 (stride plane_bytes); else dst is the pixel's
 //   row in the output tile and chunk c lands 32 bytes further
-template <int STAGE, int NCH, bool PLANES>
-__device__ __forceinline__ void epi_block(const BtArgs &a, uint32_t taddr, bool keep, bool store, uint8_t *dst, size_t plane_bytes) {
-    auto chunk = [&](auto ch_tag) {
-        constexpr int CH = decltype(ch_tag)::value;
-        uint32_t rr[16];
-        tc_ld16(taddr + 16 * CH, rr);
-        tc_wait_ld();
-        uint4 lo, hi;
-        epi16<STAGE, CH>(a, rr, keep, lo, hi);
-        if (store) {
-            if (PLANES) {
-                *reinterpret_cast<uint4 *>(dst + (size_t)(2 * CH) * plane_bytes) = lo;
-                *reinterpret_cast<uint4 *>(dst + (size_t)(2 * CH + 1) * plane_bytes) = hi;
-            } else {
-                reinterpret_cast<uint4 *>(dst + 32 * CH)[0] = lo;
-                reinterpret_cast<uint4 *>(dst + 32 * CH)[1] = hi;
-            }
+struct EpiBlk { uint32_t taddr; bool keep, store; uint8_t *dst; };
+
+template <int STAGE, int CH, bool PLANES>
+__device__ __forceinline__ void epi_store(const BtArgs &a, const uint32_t (&rr)[16], const EpiBlk &k, size_t plane_bytes) {
+    uint4 lo, hi;
+    epi16<STAGE, CH>(a, rr, k.keep, lo, hi);
+    if (k.store) {
+        if (PLANES) {
+            *reinterpret_cast<uint4 *>(k.dst + (size_t)(2 * CH) * plane_bytes) = lo;
+            *reinterpret_cast<uint4 *>(k.dst + (size_t)(2 * CH + 1) * plane_bytes) = hi;
+        } else {
+            reinterpret_cast<uint4 *>(k.dst + 32 * CH)[0] = lo;
+            reinterpret_cast<uint4 *>(k.dst + 32 * CH)[1] = hi;
         }
-    };
-    chunk(std::integral_constant<int, 0>{});
-    if constexpr (NCH > 1) chunk(std::integral_constant<int, 1>{});
-    if constexpr (NCH > 2) chunk(std::integral_constant<int, 2>{});
-    if constexpr (NCH > 3) chunk(std::integral_constant<int, 3>{});
+    }
+}
+template <int STAGE, int CH0, int CH1, bool PLANES>
+__device__ __forceinline__ void epi_pair(const BtArgs &a, const EpiBlk &k0, const EpiBlk &k1, size_t plane_bytes) {
+    uint32_t r0[16], r1[16];
+    tc_ld16(k0.taddr + 16 * CH0, r0);
+    tc_ld16(k1.taddr + 16 * CH1, r1);
+    tc_wait_ld();
+    epi_store<STAGE, CH0, PLANES>(a, r0, k0, plane_bytes);
+    epi_store<STAGE, CH1, PLANES>(a, r1, k1, plane_bytes);
+}
+template <int STAGE, int CH, bool PLANES>
+__device__ __forceinline__ void epi_single(const BtArgs &a, const EpiBlk &k, size_t plane_bytes) {
+    uint32_t r0[16];
+    tc_ld16(k.taddr + 16 * CH, r0);
+    tc_wait_ld();
+    epi_store<STAGE, CH, PLANES>(a, r0, k, plane_bytes);
+}
+
+// One epilogue stage of a warp: its M blocks are g, g + G, g + 2G, ... (G groups of four warps); `blk(b)` describes block b.
+// 16-channel stages pair two BLOCKS per wait, wider stages pair two CHUNKS of one block.
+template <int STAGE, int NCH, bool PLANES, int G, typename F>
+__device__ __forceinline__ void epi_stage(const BtArgs &a, int nb, int g, uint64_t *acc_full, uint32_t parity, size_t plane_bytes, F &&blk) {
+    if constexpr (NCH == 1) {
+        for (int b = g; b < nb; b += 2 * G) {
+            const bool two = b + G < nb;                             // warp-uniform
+            mbar_wait(&acc_full[two ? b + G : b], parity);           // blocks complete in order
+            __syncwarp();
+            tc_fence_after();
+            const EpiBlk k0 = blk(b);
+            if (two) epi_pair<STAGE, 0, 0, PLANES>(a, k0, blk(b + G), plane_bytes);
+            else epi_single<STAGE, 0, PLANES>(a, k0, plane_bytes);
+        }
+    } else {
+        for (int b = g; b < nb; b += G) {
+            mbar_wait(&acc_full[b], parity);
+            __syncwarp();
+            tc_fence_after();
+            const EpiBlk k = blk(b);
+            epi_pair<STAGE, 0, 1, PLANES>(a, k, k, plane_bytes);
+            if constexpr (NCH == 3) epi_single<STAGE, 2, PLANES>(a, k, plane_bytes);
+            if constexpr (NCH == 4) epi_pair<STAGE, 2, 3, PLANES>(a, k, k, plane_bytes);
+        }
+    }
 }
 
 template <typename F>
@@ -271,17 +307,13 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             uint8_t *A1j = A1 + (size_t)(j & 1) * a.a1_stride;
             if (warp == 0) BT_TL(0, j, 0);
             with_nch(a.s1.n, [&](auto nch) {
-                for (int b = g; b < a.s1.nb; b += kBtEpiGroups) {
-                    mbar_wait(&acc1_full[b], par_);
-                    __syncwarp();
-                    tc_fence_after();
+                epi_stage<0, decltype(nch)::value, true, kBtEpiGroups>(a, a.s1.nb, g, acc1_full, par_, (size_t)a.Pn1 * 16, [&](int b) {
                     const int m = b * 128 + q * 32 + lane;
                     const int r = (int)__umulhi((unsigned)m, a.pitch_magic), c = m - r * a.pitch;
                     const int y = y0 - 1 + r, x = x0 - 1 + c;
                     const bool inside = r < a.Th + 2 && y >= 0 && y < a.H && x >= 0 && x < a.W;
-                    epi_block<0, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.n), inside, true,
-                                                             A1j + (size_t)m * 16, (size_t)a.Pn1 * 16);
-                }
+                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.n), inside, true, A1j + (size_t)m * 16};
+                });
             });
             // warps without a block of their own still pace themselves on the stage (a free-running warp would
             // arrive on e1_done for FUTURE tiles and corrupt the phase counts)
@@ -297,15 +329,10 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             const uint32_t par_ = (uint32_t)(j & 1);
             if (warp == 0) BT_TL(0, j, 2);
             with_nch(a.s2.n, [&](auto nch) {
-                for (int b = g; b < a.s2.nb; b += kBtEpiGroups) {
-                    mbar_wait(&acc2_full[b], par_);
-                    if (warp == 0 && b == g) BT_TL(0, j, 3);
-                    __syncwarp();
-                    tc_fence_after();
+                epi_stage<1, decltype(nch)::value, true, kBtEpiGroups>(a, a.s2.nb, g, acc2_full, par_, (size_t)a.Pn2 * 16, [&](int b) {
                     const int m = b * 128 + q * 32 + lane;
-                    epi_block<1, decltype(nch)::value, true>(a, tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n), true, true,
-                                                             A2 + (size_t)m * 16, (size_t)a.Pn2 * 16);
-                }
+                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n), true, true, A2 + (size_t)m * 16};
+                });
             });
             mbar_wait(&acc2_full[a.s2.nb - 1], par_);
             fence_async_smem();
@@ -321,17 +348,13 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             if (warp == 0) BT_TL(0, j, 5);
             if (j >= 1) mbar_wait(o_free, (uint32_t)((j - 1) & 1));          // tile j-1 has left the staging tile
             with_nch(a.s3.n, [&](auto nch) {
-                for (int b = g; b < a.s3.nb; b += kBtEpiGroups) {
-                    mbar_wait(&acc3_full[b], par_);
-                    if (warp == 0 && b == g) BT_TL(0, j, 6);
-                    __syncwarp();
-                    tc_fence_after();
+                epi_stage<2, decltype(nch)::value, false, kBtEpiGroups>(a, a.s3.nb, g, acc3_full, par_, 0, [&](int b) {
                     const int m = b * 128 + q * 32 + lane;
                     const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
                     const bool valid = ro < a.Th && co < a.Tw;
-                    epi_block<2, decltype(nch)::value, false>(a, tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, valid,
-                                                              OT + ((size_t)(ro * a.Tw + co) * a.s3.n) * 2, 0);
-                }
+                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, valid,
+                                  OT + ((size_t)(ro * a.Tw + co) * a.s3.n) * 2};
+                });
             });
             mbar_wait(&acc3_full[a.s3.nb - 1], par_);
             fence_async_smem();
