@@ -365,12 +365,16 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         };
         // Schedule (see the MMA warp): while S2(i) runs, E1(i+1) fills the OTHER A1 buffer and E3(i-1) drains R3; E2(i)
         // follows S2(i) block by block.
+        // With a single A1 (blocks whose weights leave no room for two) E1(i+1) must not start before S2(i) has read the
+        // buffer, i.e. it follows E2(i) -- same issue order on the MMA side, less overlap.
         if (n_my > 0) {
+            const bool a1_double = a.a1_stride != 0;
             if (a.has_s1) E1(0);
             for (long long i = 0; i < n_my; ++i) {
-                if (a.has_s1 && i + 1 < n_my) E1(i + 1);
+                if (a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
                 if (i >= 1) E3(i - 1);
                 E2(i);
+                if (!a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
             }
             E3(n_my - 1);
         }
@@ -817,7 +821,7 @@ struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, cols; size_t bytes; };
 
 // shared-memory / TMEM footprint of a candidate tile; plane strides are multiples of 8 positions so that every
 // plane starts 128-byte aligned (TMA destination)
-static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t smem_max, BtGeom &g) {
+static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t smem_max, int a1_bufs, BtGeom &g) {
     const BtArgs &a = fb.args;
     const int pitch = tw + 2;
     const int n1 = a.has_s1 ? a.s1.n : 0, n2 = a.s2.n, n3 = a.s3.n;
@@ -833,7 +837,7 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
     size_t off = (size_t)fb.w_bytes + (size_t)fb.par_floats * 4;
     off = (off + 127) / 128 * 128;
     if (a.has_s1) off += (size_t)g.Pn0 * (a.s1.ksteps * 2) * 16;
-    off += 2 * (((size_t)g.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128);     // A1 is double-buffered
+    off += a1_bufs * (((size_t)g.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128);
     off += (size_t)g.Pn2 * (a.s3.ksteps * 2) * 16;
     off += ((size_t)th * tw * n3 * 2 + 127) / 128 * 128;
     if (a.load_kind == 0) off += 1024;
@@ -846,7 +850,7 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
 // costs about the same: its 4 KB A operand read) plus a fixed per-tile term for the hand-offs (measured: a tile costs a few thousand cycles of
 // pipeline latency whatever its size, so fewer, larger tiles win); partial
 // edge tiles are charged in full.  Tiles are even-sized so that the store warp can carry the 2x2 max-pool.
-static double bt_best_tile(const FusedBlock &fb, int H, int W, int cols_max, size_t smem_max, int &bTh, int &bTw) {
+static double bt_best_tile(const FusedBlock &fb, int H, int W, int cols_max, size_t smem_max, int a1_bufs, int &bTh, int &bTw) {
     const BtArgs &a = fb.args;
     double best = -1.0;
     BtGeom g{};
@@ -854,7 +858,7 @@ static double bt_best_tile(const FusedBlock &fb, int H, int W, int cols_max, siz
         if (th > H + 1) break;
         for (int tw = 8; tw <= 254; tw += 2) {
             if (tw > W + 1 && tw > 8) break;
-            if (!bt_geom(fb, th, tw, cols_max, smem_max, g)) continue;
+            if (!bt_geom(fb, th, tw, cols_max, smem_max, a1_bufs, g)) continue;
             const double tiles = (double)((W + tw - 1) / tw) * ((H + th - 1) / th);
             const double per_tile = (a.has_s1 ? g.nb1 * a.s1.ksteps : 0) + g.nb2 * (9.0 * a.s2.ksteps + a.s3.ksteps) + 60.0;
             const double cost = tiles * per_tile;
@@ -869,21 +873,28 @@ static double bt_best_tile(const FusedBlock &fb, int H, int W, int cols_max, siz
 static bool bt_plan(FusedBlock &fb, int H, int W) {
     BtArgs &a = fb.args;
     a.H = H; a.W = W;
-    int th1 = 0, tw1 = 0, th2 = 0, tw2 = 0;
-    const double c1 = bt_best_tile(fb, H, W, 512, kBtSmemMax, th1, tw1);
-    const double c2 = bt_best_tile(fb, H, W, 256, kBtSmemMax2, th2, tw2);
+    // candidates: {1 CTA/SM, A1 double} (the pipelined schedule), {1 CTA/SM, A1 single} when the weights leave no room
+    // for a decent tile with two buffers (chain of three only: the chain of two loads into A1 and needs both),
+    // {2 CTAs/SM} only when nothing else fits.  Measured (HeLa, r01): two co-resident half-size pipelines do not beat
+    // one full-size pipeline -- the epilogue warps of both CTAs share the same issue slots.
+    int thd = 0, twd = 0, ths = 0, tws = 0, th2 = 0, tw2 = 0;
+    const double cd = bt_best_tile(fb, H, W, 512, kBtSmemMax, 2, thd, twd);
+    const double cs = a.has_s1 ? bt_best_tile(fb, H, W, 512, kBtSmemMax, 1, ths, tws) : -1.0;
+    const double c2 = bt_best_tile(fb, H, W, 256, kBtSmemMax2, 2, th2, tw2);
     int force = 0;
     if (const char *v = getenv("IMK_BT_CTAS"); v && v[0]) force = atoi(v);
-    // measured (HeLa, r01): two co-resident half-size pipelines do not beat one full-size pipeline (the epilogue warps of
-    // both CTAs share the same issue slots), so the 2-CTA shape is used only when nothing fits the 1-CTA budget
-    bool two = c2 > 0 && c1 < 0;
-    if (force == 1 && c1 > 0) two = false;
-    if (force == 2 && c2 > 0) two = true;
-    if (!two && c1 < 0) return false;
+    int mode = -1;                                                    // 0: double, 1: single, 2: two CTAs
+    if (cd > 0) mode = 0;
+    if (cs > 0 && (mode < 0 || cs * 1.25 < cd)) mode = 1;             // the overlap is worth about a quarter of the tile time
+    if (mode < 0 && c2 > 0) mode = 2;
+    if (force == 2 && c2 > 0) mode = 2;
+    if (mode < 0) return false;
+    const bool two = mode == 2;
+    const int a1_bufs = mode == 1 ? 1 : 2;
     fb.ctas_per_sm = two ? 2 : 1;
-    const int bTh = two ? th2 : th1, bTw = two ? tw2 : tw1;
+    const int bTh = mode == 0 ? thd : (mode == 1 ? ths : th2), bTw = mode == 0 ? twd : (mode == 1 ? tws : tw2);
     BtGeom g{};
-    bt_geom(fb, bTh, bTw, two ? 256 : 512, two ? kBtSmemMax2 : kBtSmemMax, g);
+    bt_geom(fb, bTh, bTw, two ? 256 : 512, two ? kBtSmemMax2 : kBtSmemMax, a1_bufs, g);
     a.Th = bTh; a.Tw = bTw; a.pitch = bTw + 2;
     a.pitch_magic = (unsigned)((0x100000000ull + a.pitch - 1) / a.pitch);
     a.tiles_x = (W + bTw - 1) / bTw; a.tiles_y = (H + bTh - 1) / bTh;
@@ -895,7 +906,8 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     size_t off = (size_t)fb.w_bytes;
     a.par_off_b = (int)off; off += (size_t)fb.par_floats * 4; off = (off + 127) / 128 * 128;
     a.a0_off = (int)off; if (a.has_s1) off += (size_t)a.Pn0 * (a.s1.ksteps * 2) * 16;
-    a.a1_off = (int)off; a.a1_stride = (int)(((size_t)a.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128); off += 2 * (size_t)a.a1_stride;
+    a.a1_off = (int)off; a.a1_stride = (int)(((size_t)a.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128); off += (size_t)a1_bufs * a.a1_stride;
+    if (a1_bufs == 1) a.a1_stride = 0;                               // single buffer: both parities alias
     a.a2_off = (int)off; off += (size_t)a.Pn2 * (a.s3.ksteps * 2) * 16;
     a.o_off = (int)off; off += ((size_t)a.Th * a.Tw * a.s3.n * 2 + 127) / 128 * 128;
     a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
@@ -986,8 +998,8 @@ int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W,
     if (rc) return rc;
     fb.ok = true;
     if (const char *v = getenv("IMK_BT_VERBOSE"); v && v[0] == '1')
-        fprintf(stderr, "[imk] fused block kind=%d %dx%d: %d CTA/SM, tile %dx%d, M blocks %d/%d, TMEM %d cols, smem %zu B, weights %d B\n", kind, H, W,
-                fb.ctas_per_sm, a.Th, a.Tw, a.s1.nb, a.s2.nb, a.s3.col + a.s3.nb * a.s3.n, fb.smem, fb.w_bytes);
+        fprintf(stderr, "[imk] fused block kind=%d %dx%d: %d CTA/SM, A1 x%d, tile %dx%d, M blocks %d/%d, TMEM %d cols, smem %zu B, weights %d B\n", kind, H, W,
+                fb.ctas_per_sm, a.a1_stride ? 2 : 1, a.Th, a.Tw, a.s1.nb, a.s2.nb, a.s3.col + a.s3.nb * a.s3.n, fb.smem, fb.w_bytes);
     return IMK_OK;
 }
 

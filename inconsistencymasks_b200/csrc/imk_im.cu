@@ -228,22 +228,24 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int C>                          // image channels at compile time (1, 3, 4; 0 = run-time)
+template <int C, int PPT>                 // image channels at compile time (1, 3, 4; 0 = run-time); pixels per consumer thread
 __global__ void __launch_bounds__(kMcThreads, 3)
 im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, int K, int n_slots,
                          const uint8_t *__restrict__ img, int c, int block_in, int block_out,
                          uint8_t *__restrict__ img_out, uint8_t *__restrict__ label_out, uint8_t *__restrict__ im_out,
                          int64_t *__restrict__ im_size, unsigned long long *__restrict__ presence) {
+    constexpr int TILE = kMcTile * PPT;   // pixels per tile; a warp owns 32 * PPT consecutive pixels of it
+    constexpr int WPX = 32 * PPT;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    // layout: [n_slots][kMcTile*K] float | lab_s[8 warps][32] | full[n_slots] | empty[n_slots]
+    // layout: [n_slots][TILE*K] float | lab_s[8 warps][WPX] | full[n_slots] | empty[n_slots]
     float *slots = reinterpret_cast<float *>(smem_raw);
-    const size_t slot_floats = (size_t)kMcTile * K;
+    const size_t slot_floats = (size_t)TILE * K;
     uint8_t *lab_s = smem_raw + (size_t)n_slots * slot_floats * sizeof(float);
-    uint64_t *full = reinterpret_cast<uint64_t *>(lab_s + 8 * 32);
+    uint64_t *full = reinterpret_cast<uint64_t *>(lab_s + 8 * WPX);
     uint64_t *empty = full + kMcMaxSlots;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_tiles = (total_px + kMcTile - 1) / kMcTile;
+    const int64_t n_tiles = (total_px + TILE - 1) / TILE;
     if (tid == 0) {
         for (int s = 0; s < n_slots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMcConsumers / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -255,8 +257,8 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
         if (lane == 0) {
             int slot = 0, round = 0;                             // ring position (no divisions on the hot path)
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int64_t p0 = tile * kMcTile;
-                const int64_t pc = min((int64_t)kMcTile, total_px - p0);
+                const int64_t p0 = tile * TILE;
+                const int64_t pc = min((int64_t)TILE, total_px - p0);
                 const uint32_t bytes = (uint32_t)(pc * K * sizeof(float));
                 for (int m = 0; m < M; ++m) {
                     if (round > 0) mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
@@ -269,57 +271,99 @@ im_multiclass_tma_kernel(ProbPtrs probs, int M, int64_t total_px, int64_t HW, in
         return;
     }
 
-    // ---------------- consumers: thread p owns pixel p of the tile ----------------
+    // ---------------- consumers: lane l of warp w owns pixels w*WPX + 32*j + l (j < PPT) of the tile ----------------
     int slot = 0;
     uint32_t phase = 0;
     const bool small = total_px < 0x7fffffffLL;                  // 32-bit image index arithmetic (64-bit division is a subroutine)
+    const int cc = C > 0 ? C : c;
+    constexpr int GROUPS = WPX / 16;                             // 16-pixel groups per warp (one 128-bit label / IM vector each)
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t p0 = tile * kMcTile;
-        const int pc = (int)min((int64_t)kMcTile, total_px - p0);
-        const bool live = tid < pc;
+        const int64_t p0 = tile * TILE;
+        const int pc = (int)min((int64_t)TILE, total_px - p0);
         const int64_t n_lo = small ? (int64_t)((uint32_t)p0 / (uint32_t)HW) : p0 / HW;
-        const bool uniform = (p0 + pc <= (n_lo + 1) * HW);
-        const int64_t n_px = live ? (uniform ? n_lo : (small ? (int64_t)((uint32_t)(p0 + tid) / (uint32_t)HW) : (p0 + tid) / HW)) : -1;
+        const bool uniform = (p0 + pc <= (n_lo + 1) * HW) && pc == TILE;   // whole tile inside one image: one RED per warp
+        const int64_t wpx = p0 + warp * WPX;                     // first pixel of this warp
+        int tp[PPT];                                             // pixel index inside the tile
+        bool live[PPT];
+        int64_t n_px[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            tp[j] = warp * WPX + 32 * j + lane;
+            live[j] = tp[j] < pc;
+            n_px[j] = live[j] ? (uniform ? n_lo : (small ? (int64_t)((uint32_t)(p0 + tp[j]) / (uint32_t)HW) : (p0 + tp[j]) / HW)) : -1;
+        }
         // the image vector this lane will blank in the epilogue: requested before the slabs are scanned, so that
         // its DRAM latency is covered by the argmax work instead of stalling the warp at the end of every tile
-        const int64_t wpx = p0 + warp * 32;                      // first pixel of this warp
-        const int cc = C > 0 ? C : c;
-        const int ig = lane >= cc ? 1 : 0, iv = lane - ig * cc;  // 16-pixel group, 16-byte vector inside it
-        const bool img_lane = img_out && lane < 2 * cc && wpx + 16 * ig < p0 + pc;
+        const int ig = lane / cc, iv = lane - ig * cc;           // 16-pixel group, 16-byte vector inside it (lanes < GROUPS * cc)
+        const bool img_lane = img_out && lane < GROUPS * cc && wpx + 16 * ig < p0 + pc;
         uint4 pix = make_uint4(0, 0, 0, 0);
         if (img_lane) pix = ldg_stream(img + (wpx + 16 * ig) * cc + 16 * iv);
-        uint32_t disagree = 0;
-        int a0 = 0;
+        uint32_t disagree[PPT];
+        int a0[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) { disagree[j] = 0; a0[j] = 0; }
         for (int m = 0; m < M; ++m) {
             mbar_wait(&full[slot], phase);
-            int arg = 0;
-            if (live) {
-                arg = argmax_row(slots + slot * slot_floats + (size_t)tid * K, K);
-                if (m == 0) a0 = arg; else disagree |= (arg != a0);
+            int arg[PPT];
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                arg[j] = 0;
+                if (live[j]) {
+                    arg[j] = argmax_row(slots + slot * slot_floats + (size_t)tp[j] * K, K);
+                    if (m == 0) a0[j] = arg[j]; else disagree[j] |= (arg[j] != a0[j]);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);            // this warp is done with the slab
             if (++slot == n_slots) { slot = 0; phase ^= 1u; }
-            if (presence)
-                warp_or_stat(presence, n_px < 0 ? -1 : n_px * M + m, live ? (1ull << (arg & 63)) : 0ull, uniform && pc == kMcTile);
+            if (presence) {
+                if (uniform) {
+                    unsigned long long bits = 0;
+#pragma unroll
+                    for (int j = 0; j < PPT; ++j) bits |= 1ull << (arg[j] & 63);
+                    warp_or_stat(presence, n_lo * M + m, bits, true);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PPT; ++j)
+                        warp_or_stat(presence, n_px[j] < 0 ? -1 : n_px[j] * M + m, live[j] ? (1ull << (arg[j] & 63)) : 0ull, false);
+                }
+            }
         }
-        warp_add_stat(im_size, n_px, live ? disagree : 0u, uniform && pc == kMcTile);
+        if (uniform) {
+            uint32_t d = 0;
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) d += disagree[j];
+            warp_add_stat(im_size, n_lo, d, true);
+        } else {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) warp_add_stat(im_size, n_px[j], live[j] ? disagree[j] : 0u, false);
+        }
 
-        // warp-local 128-bit epilogue over the warp's 32 consecutive pixels
-        const uint32_t im_mask = __ballot_sync(0xffffffffu, live && disagree);
-        lab_s[warp * 32 + lane] = (live && !disagree) ? (uint8_t)a0 : 0;
+        // warp-local 128-bit epilogue over the warp's WPX consecutive pixels
+        uint32_t im_mask[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            im_mask[j] = __ballot_sync(0xffffffffu, live[j] && disagree[j]);
+            lab_s[warp * WPX + 32 * j + lane] = (live[j] && !disagree[j]) ? (uint8_t)a0[j] : 0;
+        }
         __syncwarp();
-        if (lane < 2 && wpx + 16 * lane < p0 + pc) {
+        auto group_bits = [&](int g) -> uint32_t {               // IM bits of 16-pixel group g of the warp
+            uint32_t word = im_mask[0];
+#pragma unroll
+            for (int j = 1; j < PPT; ++j) if ((g >> 1) == j) word = im_mask[j];
+            return (word >> (16 * (g & 1))) & 0xFFFFu;
+        };
+        if (lane < GROUPS && wpx + 16 * lane < p0 + pc) {
             const int64_t px = wpx + 16 * lane;
-            const uint32_t bits = im_mask >> (16 * lane);
+            const uint32_t bits = group_bits(lane);
             uint32_t imw[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(bits4_to_bytes01(bits >> (4 * j)));
-            stg_stream(label_out + px, *reinterpret_cast<const uint4 *>(lab_s + warp * 32 + 16 * lane));   // 0 where the IM is set
+            stg_stream(label_out + px, *reinterpret_cast<const uint4 *>(lab_s + warp * WPX + 16 * lane));   // 0 where the IM is set
             stg_stream(im_out + px, make_uint4(imw[0], imw[1], imw[2], imw[3]));
         }
         if (img_lane) {
-            const uint32_t bits = block_in ? (im_mask >> (16 * ig)) : 0u;
+            const uint32_t bits = block_in ? group_bits(ig) : 0u;
             uint32_t imw[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(bits4_to_bytes01(bits >> (4 * j)));
@@ -502,28 +546,32 @@ extern "C" int imk_im_multiclass(const float *const *probs_dev, int M, int64_t N
         presence = g_presence;
         IMK_CUDA(cudaMemsetAsync(presence, 0, need, stream));
     }
-    // ring depth / residency: prefer 3 CTAs per SM (24 consumer warps hide the shared-memory latency of
-    // the argmax scan) with at least a double buffer each; fall back to 2, then 1 CTA for wide K
-    const size_t slab_bytes = (size_t)kMcTile * K * sizeof(float);
+    // two pixels per consumer thread for narrow rows (the per-tile hand-off -- barrier waits, ballots, statistics -- is
+    // then paid once per 512 pixels); ring depth / residency: prefer 3 CTAs per SM (24 consumer warps hide the
+    // shared-memory latency of the argmax scan) with at least a double buffer each; fall back to 2, then 1 CTA for wide K
+    const int ppt = K <= 16 ? 2 : 1;
+    const int tile_px = kMcTile * ppt;
+    const size_t slab_bytes = (size_t)tile_px * K * sizeof(float);
     int n_slots = 0, per_sm = 1;
     for (int ctas = 3; ctas >= 1 && n_slots < 2; --ctas) {
         per_sm = ctas;
         n_slots = (int)(((size_t)216 * 1024 / ctas - 1024) / slab_bytes);
     }
     if (n_slots > kMcMaxSlots) n_slots = kMcMaxSlots;
-    const bool tma = vec && n_slots >= 2;
+    const bool tma = vec && n_slots >= 2 && (c * ppt <= 8);          // image lanes: 2 * ppt groups of c vectors
     {
     IMK_PROFILE(tma ? "im_multiclass_tma" : "im_multiclass_generic", -1, stream);
     if (tma) {
-        const size_t smem = (size_t)n_slots * slab_bytes + 8 * 32 + 2 * kMcMaxSlots * sizeof(uint64_t);
-        const int grid = grid_for((total + kMcTile - 1) / kMcTile, 1, per_sm);
-#define IMK_LAUNCH_MC(CC)                                                                                                          \
+        const size_t smem = (size_t)n_slots * slab_bytes + 8 * 32 * ppt + 2 * kMcMaxSlots * sizeof(uint64_t);
+        const int grid = grid_for((total + tile_px - 1) / tile_px, 1, per_sm);
+#define IMK_LAUNCH_MC(CC, PP)                                                                                                      \
         do {                                                                                                                       \
-            IMK_CUDA(cudaFuncSetAttribute(im_multiclass_tma_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-            im_multiclass_tma_kernel<CC><<<grid, kMcThreads, smem, stream>>>(pp, M, total, HW, K, n_slots, img_dev, c, block_in,    \
-                                                                             block_out, img_out_dev, label_dev, im_dev, im_size_dev, presence); \
+            IMK_CUDA(cudaFuncSetAttribute(im_multiclass_tma_kernel<CC, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            im_multiclass_tma_kernel<CC, PP><<<grid, kMcThreads, smem, stream>>>(pp, M, total, HW, K, n_slots, img_dev, c, block_in, \
+                                                                                 block_out, img_out_dev, label_dev, im_dev, im_size_dev, presence); \
         } while (0)
-        if (c == 3) IMK_LAUNCH_MC(3); else if (c == 1) IMK_LAUNCH_MC(1); else if (c == 4) IMK_LAUNCH_MC(4); else IMK_LAUNCH_MC(0);
+        if (ppt == 2) { if (c == 3) IMK_LAUNCH_MC(3, 2); else if (c == 1) IMK_LAUNCH_MC(1, 2); else if (c == 4) IMK_LAUNCH_MC(4, 2); else IMK_LAUNCH_MC(0, 2); }
+        else          { if (c == 3) IMK_LAUNCH_MC(3, 1); else if (c == 1) IMK_LAUNCH_MC(1, 1); else if (c == 4) IMK_LAUNCH_MC(4, 1); else IMK_LAUNCH_MC(0, 1); }
 #undef IMK_LAUNCH_MC
     } else {
         const int grid = grid_for(total, 256, 8);
