@@ -884,10 +884,20 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     int force = 0;
     if (const char *v = getenv("IMK_BT_CTAS"); v && v[0]) force = atoi(v);
     int mode = -1;                                                    // 0: double, 1: single, 2: two CTAs
-    if (cd > 0) mode = 0;
-    if (cs > 0 && (mode < 0 || cs * 1.25 < cd)) mode = 1;             // the overlap is worth about a quarter of the tile time
+    if (const char *v = getenv("IMK_BT_TILE"); v && v[0]) {           // tuning aid: "kind:H:th:tw[;...]" pins the tile of a block
+        int k_, h_, th_, tw_;
+        for (const char *p = v; p && *p; p = strchr(p, ';') ? strchr(p, ';') + 1 : nullptr)
+            if (sscanf(p, "%d:%d:%d:%d", &k_, &h_, &th_, &tw_) == 4 && k_ == a.load_kind && h_ == H) {
+                BtGeom gg{};
+                if (bt_geom(fb, th_, tw_, 512, kBtSmemMax, 2, gg)) { thd = th_; twd = tw_; mode = 0; }
+                else if (a.has_s1 && bt_geom(fb, th_, tw_, 512, kBtSmemMax, 1, gg)) { ths = th_; tws = tw_; mode = 1; }
+            }
+    }
+    const bool pinned = mode >= 0;
+    if (mode < 0 && cd > 0) mode = 0;
+    if (!pinned && cs > 0 && (mode < 0 || cs * 1.25 < cd)) mode = 1;  // the overlap is worth about a quarter of the tile time
     if (mode < 0 && c2 > 0) mode = 2;
-    if (force == 2 && c2 > 0) mode = 2;
+    if (!pinned && force == 2 && c2 > 0) mode = 2;
     if (mode < 0) return false;
     const bool two = mode == 2;
     const int a1_bufs = mode == 1 ? 1 : 2;

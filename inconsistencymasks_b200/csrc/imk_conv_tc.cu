@@ -30,8 +30,8 @@
 namespace imk {
 
 constexpr int kTcThreads = 160;          // warps 0-3: strip load + epilogue (TMEM lanes 32w..32w+31); warp 4: + bulk copies, MMA issue
-constexpr int kWSlots = 3;
-constexpr int kWStageMax = 32 * 1024;
+constexpr int kWSlots = 6;
+constexpr int kWStageMax = 16 * 1024;
 constexpr int kMaxMBlocks = 32;          // 512 TMEM columns / 16 output channels
 
 struct TcArgs {
@@ -42,6 +42,7 @@ struct TcArgs {
     int H, W, cin_p, cout_p, taps, halo, pitch, Th, n_mblocks, Pn, tmem_cols;
     int units_total, units_per_stage, unit_bytes, ksteps, n_stages;
     int act_bytes, stage_bytes;
+    long long *dbg;                         // optional timeline of CTA (0,0) (IMK_TC_TIMELINE=1): 8 clock64 stamps
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------
@@ -108,7 +109,12 @@ conv_tc_kernel(const TcArgs a) {
     const int64_t n = blockIdx.y;
     const int y0 = strip * a.Th;
     const int KC = a.cin_p >> 3;
+#define TC_TL(ev) do { if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) a.dbg[ev] = clock64(); } while (0)
+    if (warp == 0) TC_TL(0);
 
+    // Measured (r01, HeLa level 3/4): streaming the ring through a 2/4/8-CTA cluster with multicast copies changes
+    // nothing -- the MMA phase is bound by the operand reads from shared memory (A and B, 8 KB per N = 128 MMA), not by
+    // the L2 -> SM weight stream -- so every CTA streams its own copy.
     if (warp == 4 && lane == 0) {
         for (int s = 0; s < kWSlots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < kMaxMBlocks; ++b) mbar_init(&acc_full[b], 1);
@@ -135,6 +141,7 @@ conv_tc_kernel(const TcArgs a) {
     {
         const int rows = a.Th + 2 * a.halo;
         const int items = rows * a.pitch * KC;                 // 16-byte items, kc fastest (coalesced global reads)
+        const unsigned kc_magic = 0xFFFFFFFFu / (unsigned)KC + 1u, pitch_magic = 0xFFFFFFFFu / (unsigned)a.pitch + 1u;   // exact for i < 2^20
         const __half *in_n = a.in + n * (int64_t)a.H * a.W * a.cin_p;
         const __half *lo_n = a.in_lo ? a.in_lo + n * (int64_t)(a.H >> 1) * (a.W >> 1) * a.cin_p : nullptr;
         if (!lo_n) {
@@ -142,9 +149,8 @@ conv_tc_kernel(const TcArgs a) {
             // image), every item of the strip in flight at once, no register staging
             const uint32_t act_u32 = smem_u32(act);
             for (int i = tid; i < items; i += kTcThreads) {
-                const int kc = i % KC;
-                const int f = i / KC;
-                const int r = f / a.pitch, c = f - r * a.pitch;
+                const int f = (int)__umulhi((unsigned)i, kc_magic), kc = i - f * KC;
+                const int r = (int)__umulhi((unsigned)f, pitch_magic), c = f - r * a.pitch;
                 const int y = y0 + r - a.halo, x = c - a.halo;
                 const bool inside = y >= 0 && y < a.H && x >= 0 && x < a.W;
                 const __half *src = inside ? in_n + ((int64_t)y * a.W + x) * a.cin_p + kc * 8 : in_n;
@@ -165,9 +171,8 @@ conv_tc_kernel(const TcArgs a) {
                     u[q] = make_uint4(0, 0, 0, 0);
                     dst[q] = -1;
                     if (i < items) {
-                        const int kc = i % KC;
-                        const int f = i / KC;
-                        const int r = f / a.pitch, c = f - r * a.pitch;
+                        const int f = (int)__umulhi((unsigned)i, kc_magic), kc = i - f * KC;
+                        const int r = (int)__umulhi((unsigned)f, pitch_magic), c = f - r * a.pitch;
                         const int y = y0 + r - a.halo, x = c - a.halo;
                         dst[q] = kc * a.Pn + f;
                         if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
@@ -193,12 +198,14 @@ conv_tc_kernel(const TcArgs a) {
             }
         }
     }
+    if (warp == 0) TC_TL(1);                    // own share of the strip has landed
     // generic-proxy writes to smem -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (warp == 0) TC_TL(2);                    // every warp's share has landed
 
     if (warp == 4) {
         if (lane == 0) {
@@ -209,42 +216,68 @@ conv_tc_kernel(const TcArgs a) {
             // SBO = distance between consecutive 8-row (8 pixels / 8 couts) core matrices
             const uint32_t a_lbo = (uint32_t)a.Pn * 16u, a_sbo = 128u;
             const uint32_t b_lbo = (uint32_t)a.cout_p * 16u, b_sbo = 128u;
-            auto issue_unit = [&](uint32_t wbase, int ul, int unit, int b) {
-                const int tap = unit / a.ksteps, j = unit - tap * a.ksteps;
-                const int dy = (a.taps == 9) ? tap / 3 : 0, dx = (a.taps == 9) ? tap - 3 * dy : 0;
-                const uint32_t a_off = (uint32_t)((2 * j) * a.Pn + dy * a.pitch + dx) * 16u;
-                const uint64_t bdesc = umma_desc(wbase + (uint32_t)ul * (uint32_t)a.unit_bytes, b_lbo, b_sbo);
-                const uint64_t adesc = umma_desc(act_base + a_off + (uint32_t)b * 2048u, a_lbo, a_sbo);
-                tc_mma_f16(tmem + (uint32_t)(b * a.cout_p), adesc, bdesc, idesc, unit > 0 ? 1u : 0u);
+            // The issue sequence of one MMA must stay far below the MMA itself (64 cycles at N = 128): descriptors are
+            // two 32-bit words each, the high words are constants, the low words advance by additions only -- the
+            // (tap, k-step) position of a unit is carried incrementally, no division on this path.
+            //   lo = (addr >> 4) | (LBO >> 4) << 16      hi = (SBO >> 4) | version 1 << 14
+            (void)a_sbo; (void)b_sbo;
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo0 = (act_base >> 4) | ((a_lbo >> 4) << 16);
+            const uint32_t b_lbo16 = (b_lbo >> 4) << 16, unit16 = (uint32_t)a.unit_bytes >> 4;
+            const uint32_t jstep = 2u * (uint32_t)a.Pn, pitch = (uint32_t)a.pitch, ncol = (uint32_t)a.cout_p;
+            const int ksteps = a.ksteps, nmb = a.n_mblocks;
+            auto mma = [&](uint32_t d, uint32_t alo, uint32_t blo, uint32_t acc) {
+                tc_mma_f16(d, ((uint64_t)kDescHi << 32) | alo, ((uint64_t)kDescHi << 32) | blo, idesc, acc);
+            };
+            struct Pos { int j, dx; uint32_t off; uint32_t row; };        // off = 2*j*Pn + dy*pitch + dx (16-byte units), row = dy*pitch
+            auto advance = [&](Pos &p) {
+                if (++p.j < ksteps) { p.off += jstep; return; }
+                p.j = 0;
+                if (a.taps == 9 && ++p.dx == 3) { p.dx = 0; p.row += pitch; }
+                p.off = p.row + (uint32_t)p.dx;
             };
             if (a.n_stages == 1) {
                 // all weights resident: finish one M block at a time so its epilogue overlaps the next block's MMAs
                 mbar_wait(&full[0], 0);
                 tc_fence_after();
-                const uint32_t wbase = smem_u32(wring);
-                for (int b = 0; b < a.n_mblocks; ++b) {
-                    for (int u = 0; u < a.units_total; ++u) issue_unit(wbase, u, u, b);
+                const uint32_t b_lo0 = (smem_u32(wring) >> 4) | b_lbo16;
+                for (int b = 0; b < nmb; ++b) {
+                    Pos p{0, 0, 0u, 0u};
+                    uint32_t blo = b_lo0;
+                    const uint32_t d = tmem + (uint32_t)b * ncol, ab = a_lo0 + (uint32_t)b * 128u;
+                    for (int u = 0; u < a.units_total; ++u, blo += unit16) { mma(d, ab + p.off, blo, u > 0 ? 1u : 0u); advance(p); }
                     tc_commit(&acc_full[b]);
                 }
             } else {
+                Pos p{0, 0, 0u, 0u};
+                uint32_t acc = 0;
+                int slot = 0;
+                uint32_t ph = 0;
                 for (int s = 0; s < a.n_stages; ++s) {
-                    const int slot = s % kWSlots;
-                    mbar_wait(&full[slot], (uint32_t)((s / kWSlots) & 1));
+                    mbar_wait(&full[slot], ph);
                     tc_fence_after();
-                    const uint32_t wbase = smem_u32(wring + slot * a.stage_bytes);
-                    for (int ul = 0; ul < a.units_per_stage; ++ul)
-                        for (int b = 0; b < a.n_mblocks; ++b) issue_unit(wbase, ul, s * a.units_per_stage + ul, b);
-                    tc_commit(&empty[slot]);                       // arrives when the MMAs above have read this slot
-                    if (s >= 1 && s - 1 + kWSlots < a.n_stages) {  // refill the slot stage s-1 used
-                        const int ps = s - 1, pslot = ps % kWSlots, ns = ps + kWSlots;
-                        mbar_wait(&empty[pslot], (uint32_t)((ps / kWSlots) & 1));
+                    uint32_t blo = (smem_u32(wring + slot * a.stage_bytes) >> 4) | b_lbo16;
+                    for (int ul = 0; ul < a.units_per_stage; ++ul, blo += unit16) {
+                        const uint32_t ab = a_lo0 + p.off;
+                        uint32_t d = tmem;
+                        for (int b = 0; b < nmb; ++b, d += ncol) mma(d, ab + (uint32_t)b * 128u, blo, acc);
+                        acc = 1;
+                        advance(p);
+                    }
+                    tc_commit(&empty[slot]);                           // arrives when the MMAs above have read this slot
+                    if (s >= 1 && s - 1 + kWSlots < a.n_stages) {      // refill the slot stage s-1 used
+                        const int ps = s - 1, pslot = slot == 0 ? kWSlots - 1 : slot - 1, ns = ps + kWSlots;
+                        const uint32_t pph = slot == 0 ? ph ^ 1u : ph;                // parity of stage ps on its slot
+                        mbar_wait(&empty[pslot], pph);
                         mbar_expect_tx(&full[pslot], (uint32_t)a.stage_bytes);
                         bulk_g2s(smem_u32(wring + pslot * a.stage_bytes),
                                  reinterpret_cast<const uint8_t *>(a.wpk) + (size_t)ns * a.stage_bytes, (uint32_t)a.stage_bytes, &full[pslot]);
                     }
+                    if (++slot == kWSlots) { slot = 0; ph ^= 1u; }
                 }
-                for (int b = 0; b < a.n_mblocks; ++b) tc_commit(&acc_full[b]);
+                for (int b = 0; b < nmb; ++b) tc_commit(&acc_full[b]);
             }
+            TC_TL(3);                           // last MMA issued
         }
         __syncwarp();
     } else {
@@ -252,6 +285,7 @@ conv_tc_kernel(const TcArgs a) {
         __half *out_n = a.out + n * (int64_t)a.H * a.W * a.cout_p;
         for (int b = 0; b < a.n_mblocks; ++b) {
             mbar_wait(&acc_full[b], 0);
+            if (warp == 0 && b == 0) TC_TL(4);  // first accumulator block final
             tc_fence_after();
             const int m = b * 128 + warp * 32 + lane;
             const int ro = m / a.pitch, co = m - ro * a.pitch;
@@ -265,10 +299,17 @@ conv_tc_kernel(const TcArgs a) {
                 if (valid) {
                     __align__(16) __half o[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float v = fmaxf(__uint_as_float(r[e]) + par[c0 + e], 0.f);
-                        v = __fmaf_rn(v, par[a.cout_p + c0 + e], par[2 * a.cout_p + c0 + e]);
-                        o[e] = __float2half_rn(v);
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const float4 pb = *reinterpret_cast<const float4 *>(par + c0 + 4 * e4);
+                        const float4 ps = *reinterpret_cast<const float4 *>(par + a.cout_p + c0 + 4 * e4);
+                        const float4 ph = *reinterpret_cast<const float4 *>(par + 2 * a.cout_p + c0 + 4 * e4);
+                        const float b4[4] = {pb.x, pb.y, pb.z, pb.w}, s4[4] = {ps.x, ps.y, ps.z, ps.w}, h4[4] = {ph.x, ph.y, ph.z, ph.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float v = fmaxf(__uint_as_float(r[4 * e4 + k]) + b4[k], 0.f);
+                            v = __fmaf_rn(v, s4[k], h4[k]);
+                            o[4 * e4 + k] = __float2half_rn(v);
+                        }
                     }
                     reinterpret_cast<uint4 *>(dst + c0)[0] = reinterpret_cast<const uint4 *>(o)[0];
                     reinterpret_cast<uint4 *>(dst + c0)[1] = reinterpret_cast<const uint4 *>(o)[1];
@@ -276,6 +317,7 @@ conv_tc_kernel(const TcArgs a) {
             }
         }
         tc_fence_before();
+        if (warp == 0) TC_TL(5);                // epilogue done
     }
     __syncthreads();
     if (warp == 0) {
@@ -330,7 +372,9 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
     a.units_total = a.taps * a.ksteps;
     a.unit_bytes = L.cout_p * 32;
     const int KC = L.cin_p / 8;
-    const double mma_cyc = std::max(39.0, L.cout_p / 2.0);          // measured: tools/ubench/mma_issue.cu
+    // measured in situ (IMK_TC_TIMELINE, r01): the tap-shifted A operand is misaligned to the 128-byte shared-memory
+    // lines and B is re-read for every M block, so an MMA costs its operand reads, about 64 + 0.8 N cycles
+    const double mma_cyc = 64.0 + 0.8 * L.cout_p;
     const double l2_trip = 1500.0;
     double best = -1.0;
     for (int stage_max = kWStageMax; stage_max >= 8 * 1024; stage_max >>= 1) {
@@ -352,7 +396,7 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
                 const double ctas = (double)((h + th - 1) / th) * (double)std::max<int64_t>(n_images, 1);
                 const double t_mma = a.units_total * nmb * mma_cyc;
                 const double t_stream = n_stages > 1 ? n_stages * std::max(U * nmb * mma_cyc, l2_trip / (kWSlots - 1)) : t_mma;
-                const double t_io = 2500.0 + nmb * (L.cout_p / 16) * 120.0;
+                const double t_io = 1500.0 + act_bytes / 12.0 + nmb * (L.cout_p / 16) * 400.0;   // strip load + epilogue, not overlapped inside a CTA
                 const double t_cta = t_io + std::max(t_mma, t_stream);
                 const double wave = resident == 2 ? std::max(2.0 * t_mma, t_cta) : t_cta;
                 const double waves = std::ceil(ctas / (double)(kNumSMs * resident));
@@ -391,8 +435,22 @@ int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __
         fprintf(stderr, "[imk] conv_tc %dx%d k%d %d->%d: strip %d rows, %d M blocks, TMEM %d cols, %d stages of %d B, act %d B\n", h, w, L.ks,
                 L.cin_p, L.cout_p, a.Th, a.n_mblocks, a.tmem_cols, a.n_stages, a.stage_bytes, a.act_bytes);
     dim3 grid((h + a.Th - 1) / a.Th, (unsigned)n);
+    static long long *dbg_dev = nullptr;
+    a.dbg = nullptr;
+    if (env_flag("IMK_TC_TIMELINE")) {
+        if (!dbg_dev) IMK_CUDA(cudaMalloc(&dbg_dev, 8 * sizeof(long long)));
+        IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(long long), stream));
+        a.dbg = dbg_dev;
+    }
     conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(a);
     IMK_LAUNCHED();
+    if (a.dbg) {
+        long long t[8];
+        IMK_CUDA(cudaStreamSynchronize(stream));
+        IMK_CUDA(cudaMemcpy(t, dbg_dev, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[imk] conv_tc timeline %dx%d k%d %d->%d (cycles): strip own %lld, all %lld, last MMA issued %lld, first block final %lld, epilogue done %lld\n",
+                h, w, L.ks, L.cin_p, L.cout_p, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0]);
+    }
     return IMK_OK;
 }
 
