@@ -308,7 +308,7 @@ def run_b200(args, rank, local_rank, world):
                                          im.data_ptr(), im_size.data_ptr(), pred_size.data_ptr(), stream))
     prof = _lib.profile_end()
     total_ms = sum(p["total_ms"] for p in prof) or 1.0
-    chunk = 64
+    chunk = min(int(lib.imk_max_chunk()), N)      # images per kernel launch of the trunk
     work = {w["layer"]: w for w in layer_work(chunk)}
     rows = []
     for p in sorted(prof, key=lambda p: -p["total_ms"]):
@@ -391,8 +391,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images-per-step", type=int, default=2048)
-    ap.add_argument("--e2e-images", type=int, default=2048)
-    ap.add_argument("--e2e-chunk", type=int, default=256)
+    ap.add_argument("--e2e-images", type=int, default=4096)
+    ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--im-images", type=int, default=1024)
     ap.add_argument("--cpu-images", type=int, default=256)
     ap.add_argument("--ref-images-per-step", type=int, default=32)

@@ -56,6 +56,8 @@ int         imk_version(void);
 const char *imk_last_error(void);
 /* Number of kernel launches this thread issued through the library so far. */
 int64_t     imk_launch_count(void);
+/* Images per internal trunk pass (the workspace of a model is sized for this many; env IMK_CHUNK overrides). */
+int64_t     imk_max_chunk(void);
 /* 1 when a CUDA device is usable from this process, else 0 (never throws). */
 int         imk_device_available(void);
 

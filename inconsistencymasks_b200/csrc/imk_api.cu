@@ -183,7 +183,8 @@ int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uin
     const int64_t HW = (int64_t)d.height * d.width;
     const int K = d.num_outputmasks;
     const int planes = multiclass ? 1 : K;
-    if (chunk <= 0) chunk = 4 * kMaxChunk;
+    // default: large chunks (kernel efficiency), but at least four of them in flight through the three slots
+    if (chunk <= 0) chunk = std::min<int64_t>(kMaxChunk, std::max<int64_t>(64, (N + 3) / 4));
     chunk = std::min<int64_t>(chunk, N);
     Pipeline &P = g_pipe;
     int rc = pipeline_reserve(P, chunk, (size_t)chunk * HW * d.in_channels, (size_t)chunk * HW, (size_t)chunk * HW * planes, planes);

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <vector>
 #include "imk_im.cuh"
+#include <stdlib.h>
 #include "imk_unet.cuh"
 
 namespace imk {
@@ -446,6 +447,21 @@ static std::vector<PlanItem> make_plan(const imk_unet_desc &d, const int f[5]) {
     conv(1, cin, d.num_outputmasks);                                          // 'out'
     return p;
 }
+
+int64_t max_chunk() {
+    static int64_t v = 0;
+    if (!v) {
+        v = 512;                             // measured (HeLa): 64 -> 35.5k, 128 -> 39.6k, 256 -> 42.5k, 512 -> 43.7k, 1024 -> 44.7k img/s
+        if (const char *e = getenv("IMK_CHUNK"); e && e[0]) v = atoll(e);
+        if (v < 1) v = 1;
+        if (v > 1024) v = 1024;
+    }
+    return v;
+}
+
+}  // namespace imk
+extern "C" int64_t imk_max_chunk(void) { return imk::max_chunk(); }
+namespace imk {
 
 int unet_reserve(imk_unet *net, int64_t n) {
     if (n <= net->cap_n) return IMK_OK;

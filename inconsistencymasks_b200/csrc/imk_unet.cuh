@@ -54,7 +54,8 @@ namespace imk {
 // output, fp16 [n,H,W,C1p]) in net->lvl[0].a.  `images` points at image n0.
 int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaStream_t stream);
 int unet_reserve(imk_unet *net, int64_t n);
-constexpr int64_t kMaxChunk = 64;       // images per trunk pass (bounds the workspace)
+int64_t max_chunk();                    // images per trunk pass (bounds the workspace; IMK_CHUNK overrides the default)
+#define kMaxChunk (imk::max_chunk())
 
 // imk_conv_tc.cu: tcgen05 implicit-GEMM engine.  Returns IMK_OK when it handled the layer.
 bool conv_tc_supported(const ConvLayer &L);

@@ -22,7 +22,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 # ncu launch list of the bench command (share of step per kernel)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/ncu_launches.csv python bench.py --steps 2 --warmup 1 --images-per-step 256 --e2e-images 64 --im-images 64 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1; echo "ncu launches exit $?"
 # ncu full: block-fused trunk kernels (one pass of one model) and the fused epilogue / IM kernels
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:block_tc -s 12 -c 12 -o $OUT/block_tc_hela python tools/trunk_probe.py --config hela --engine fused > $OUT/ncu_block.log 2>&1; echo "ncu block exit $?"; tail -2 $OUT/ncu_block.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:block_tc -s 6 -c 6 -o $OUT/block_tc_hela python tools/trunk_probe.py --config hela --engine fused > $OUT/ncu_block.log 2>&1; echo "ncu block exit $?"; tail -2 $OUT/ncu_block.log
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:ensemble_im -s 1 -c 1 -o $OUT/ens_hela python bench.py --steps 1 --warmup 1 --images-per-step 64 --e2e-images 64 --im-images 64 --no-cpu-baseline > $OUT/ncu_ens.log 2>&1; echo "ncu ens exit $?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:im_binary_vec -s 3 -c 1 -o $OUT/im_hela python tools/im_kernel_bench.py --config hela --images 512 --iters 5 > $OUT/ncu_hela.log 2>&1; echo "ncu im hela exit $?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:im_multiclass -s 3 -c 1 -o $OUT/im_suim python tools/im_kernel_bench.py --config suim --images 256 --iters 5 > $OUT/ncu_suim.log 2>&1; echo "ncu im suim exit $?"
