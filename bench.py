@@ -319,21 +319,29 @@ def run_b200(args, rank, local_rank, world):
             row.update(gbs=wk["bytes"] / avg_ms / 1e6, tflops=wk["flops"] / avg_ms / 1e9, bytes=wk["bytes"], flops=wk["flops"])
         rows.append(row)
     top = rows[0]
+    # dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (scaled to this launch's images)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(f"{top['kernel']}:{top['layer']}")
+        if t:
+            traffic = float(t["bytes_per_image"]) * chunk
     if "gbs" in top:
         ai = top["flops"] / top["bytes"]
         ridge = pk["tf_sustained"] * 1e12 / (pk["hbm"] * 1e9)
         if ai > ridge:
             roof = dict(bound="tensor", achieved=top["tflops"], peak=pk["tf_sustained"], unit="TFLOP/s",
-                        frac=top["tflops"] / pk["tf_sustained"], traffic=None)
+                        frac=top["tflops"] / pk["tf_sustained"], traffic=traffic)
         else:
-            roof = dict(bound="hbm", achieved=top["gbs"], peak=pk["hbm"], unit="GB/s", frac=top["gbs"] / pk["hbm"], traffic=None)
+            roof = dict(bound="hbm", achieved=top["gbs"], peak=pk["hbm"], unit="GB/s", frac=top["gbs"] / pk["hbm"], traffic=traffic)
         roof.update(kernel=top["kernel"], layer=top["layer"], share_of_step=top["share"], avg_us=top["avg_us"],
-                    tflops=top["tflops"], gbs=top["gbs"], peak_source=pk["source"] + " (sustained bf16 / copy)")
+                    tflops=top["tflops"], gbs=top["gbs"], peak_source=pk["source"] + " (sustained bf16 / copy)",
+                    algorithmic_bytes=top["bytes"], images_per_launch=chunk)
     else:
         # dominant kernel is the fused epilogue: reads M fp16 c9 maps + image, writes 5 uint8 maps
         b = chunk * H * W * (2 * 16 * M + CIN + CIN + K + 1)
         gbs = b / (top["avg_us"] * 1e-6) / 1e9
-        roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=None,
+        roof = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=traffic,
                     kernel=top["kernel"], layer=top["layer"], share_of_step=top["share"], avg_us=top["avg_us"],
                     peak_source=pk["source"])
 
