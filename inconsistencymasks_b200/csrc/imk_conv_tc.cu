@@ -42,6 +42,7 @@ struct TcArgs {
     int H, W, cin_p, cout_p, taps, halo, pitch, Th, n_mblocks, Pn, tmem_cols;
     int units_total, units_per_stage, unit_bytes, ksteps, n_stages;
     int act_bytes, stage_bytes;
+    int out_cstride, out_coff;              // channels of the whole output map / first channel of this launch (N split of wide layers)
     long long *dbg;                         // optional timeline of CTA (0,0) (IMK_TC_TIMELINE=1): 8 clock64 stamps
 };
 
@@ -282,7 +283,7 @@ conv_tc_kernel(const TcArgs a) {
         __syncwarp();
     } else {
         // ---- epilogue: TMEM -> registers -> bias, ReLU, BN -> fp16 -> global ------------------
-        __half *out_n = a.out + n * (int64_t)a.H * a.W * a.cout_p;
+        __half *out_n = a.out + n * (int64_t)a.H * a.W * a.out_cstride + a.out_coff;
         for (int b = 0; b < a.n_mblocks; ++b) {
             mbar_wait(&acc_full[b], 0);
             if (warp == 0 && b == 0) TC_TL(4);  // first accumulator block final
@@ -291,7 +292,7 @@ conv_tc_kernel(const TcArgs a) {
             const int ro = m / a.pitch, co = m - ro * a.pitch;
             const int y = y0 + ro;
             const bool valid = co < a.W && ro < a.Th && y < a.H;
-            __half *dst = out_n + ((int64_t)y * a.W + co) * a.cout_p;
+            __half *dst = out_n + ((int64_t)y * a.W + co) * a.out_cstride;
             for (int c0 = 0; c0 < a.cout_p; c0 += 16) {
                 uint32_t r[16];
                 tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * a.cout_p + c0), r);
@@ -332,19 +333,24 @@ static int env_flag(const char *name) {
     return (v && v[0] && v[0] != '0') ? 1 : 0;
 }
 
+// Layers wider than the UMMA N limit (256) run as two launches over halves of the output channels (the bottleneck
+// 3x3 of the alpha = 2 networks, 256 -> 512): each half has its own operand-B image, bias / BN slice and channel offset.
+static int tc_parts(const ConvLayer &L) { return L.cout_p <= 256 ? 1 : 2; }
+
 bool conv_tc_supported(const ConvLayer &L) {
     if (env_flag("IMK_TC_DISABLE")) return false;
-    return (L.ks == 1 || L.ks == 3) && L.cin_p % 16 == 0 && L.cout_p % 16 == 0 && L.cout_p <= 256 && L.cin_p <= 1024;
+    return (L.ks == 1 || L.ks == 3) && L.cin_p % 16 == 0 && L.cout_p % 16 == 0 && L.cout_p <= 512 && (L.cout_p / tc_parts(L)) % 16 == 0 &&
+           L.cin_p <= 1024;
 }
 
-// operand-B image: [tap][kc = cin_p/8][cout_p][8] fp16 (zero in the padding)
+// operand-B image per N part: [tap][kc = cin_p/8][cout_p / parts][8] fp16 (zero in the padding), parts back to back
 int conv_tc_pack(ConvLayer &L, const float *hwio, std::vector<void *> &owned) {
-    const int taps = L.ks * L.ks, KC = L.cin_p / 8;
+    const int taps = L.ks * L.ks, KC = L.cin_p / 8, parts = tc_parts(L), pn = L.cout_p / parts;
     std::vector<__half> w((size_t)taps * KC * L.cout_p * 8, __float2half(0.f));
     for (int tap = 0; tap < taps; ++tap)
         for (int ci = 0; ci < L.cin; ++ci)
             for (int co = 0; co < L.cout; ++co)
-                w[(((size_t)tap * KC + ci / 8) * L.cout_p + co) * 8 + (ci & 7)] =
+                w[(size_t)(co / pn) * taps * KC * pn * 8 + (((size_t)tap * KC + ci / 8) * pn + co % pn) * 8 + (ci & 7)] =
                     __float2half_rn(hwio[((size_t)tap * L.cin + ci) * L.cout + co]);
     void *p = nullptr;
     if (cudaMalloc(&p, w.size() * sizeof(__half)) != cudaSuccess) { set_error("conv_tc_pack: cudaMalloc failed"); return IMK_ENOMEM; }
@@ -415,16 +421,22 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
 
 bool conv_tc_fits(const ConvLayer &L, int h, int w) {
     TcArgs a{};
-    return conv_tc_supported(L) && L.w_umma && tc_plan(L, h, w, 64, a);
+    if (!conv_tc_supported(L) || !L.w_umma) return false;
+    ConvLayer Lp = L;
+    Lp.cout_p = L.cout_p / tc_parts(L);
+    return tc_plan(Lp, h, w, 64, a);
 }
 
 int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __half *out, __half *pool_out,
                    int64_t n, int h, int w, cudaStream_t stream) {
     (void)pool_out;
+    const int parts = tc_parts(L);
+    ConvLayer Lp = L;
+    Lp.cout_p = L.cout_p / parts;
     TcArgs a{};
-    if (!tc_plan(L, h, w, n, a)) { set_error("conv_tc_launch: no strip configuration fits (cin_p=%d cout_p=%d %dx%d)", L.cin_p, L.cout_p, h, w); return IMK_ESTATE; }
-    a.in = in; a.in_lo = in_lo; a.out = out; a.wpk = L.w_umma;
-    a.bias = L.bias; a.bn_scale = L.has_bn ? L.bn_scale : nullptr; a.bn_shift = L.bn_shift;
+    if (!tc_plan(Lp, h, w, n, a)) { set_error("conv_tc_launch: no strip configuration fits (cin_p=%d cout_p=%d %dx%d)", L.cin_p, L.cout_p, h, w); return IMK_ESTATE; }
+    a.in = in; a.in_lo = in_lo; a.out = out;
+    a.out_cstride = L.cout_p;
     const size_t smem = (size_t)a.act_bytes + kWSlots * a.stage_bytes + 3 * a.cout_p * 4 + (2 * kWSlots + kMaxMBlocks) * 8 + 16;
     static size_t attr_set = 0;
     if (smem > attr_set) {
@@ -436,20 +448,27 @@ int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __
                 L.cin_p, L.cout_p, a.Th, a.n_mblocks, a.tmem_cols, a.n_stages, a.stage_bytes, a.act_bytes);
     dim3 grid((h + a.Th - 1) / a.Th, (unsigned)n);
     static long long *dbg_dev = nullptr;
-    a.dbg = nullptr;
-    if (env_flag("IMK_TC_TIMELINE")) {
-        if (!dbg_dev) IMK_CUDA(cudaMalloc(&dbg_dev, 8 * sizeof(long long)));
-        IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(long long), stream));
-        a.dbg = dbg_dev;
-    }
-    conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(a);
-    IMK_LAUNCHED();
-    if (a.dbg) {
-        long long t[8];
-        IMK_CUDA(cudaStreamSynchronize(stream));
-        IMK_CUDA(cudaMemcpy(t, dbg_dev, sizeof(t), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[imk] conv_tc timeline %dx%d k%d %d->%d (cycles): strip own %lld, all %lld, last MMA issued %lld, first block final %lld, epilogue done %lld\n",
-                h, w, L.ks, L.cin_p, L.cout_p, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0]);
+    for (int part = 0; part < parts; ++part) {
+        a.out_coff = part * Lp.cout_p;
+        a.wpk = L.w_umma + (size_t)part * L.ks * L.ks * L.cin_p * Lp.cout_p;
+        a.bias = L.bias + a.out_coff;
+        a.bn_scale = L.has_bn ? L.bn_scale + a.out_coff : nullptr;
+        a.bn_shift = L.has_bn ? L.bn_shift + a.out_coff : nullptr;
+        a.dbg = nullptr;
+        if (env_flag("IMK_TC_TIMELINE")) {
+            if (!dbg_dev) IMK_CUDA(cudaMalloc(&dbg_dev, 8 * sizeof(long long)));
+            IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(long long), stream));
+            a.dbg = dbg_dev;
+        }
+        conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(a);
+        IMK_LAUNCHED();
+        if (a.dbg) {
+            long long t[8];
+            IMK_CUDA(cudaStreamSynchronize(stream));
+            IMK_CUDA(cudaMemcpy(t, dbg_dev, sizeof(t), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[imk] conv_tc timeline %dx%d k%d %d->%d (cycles): strip own %lld, all %lld, last MMA issued %lld, first block final %lld, epilogue done %lld\n",
+                    h, w, L.ks, L.cin_p, Lp.cout_p, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0]);
+        }
     }
     return IMK_OK;
 }

@@ -239,7 +239,11 @@ __device__ __forceinline__ void pixel_probs(const __half *__restrict__ x /*c1p h
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
-                const float *wk = w_s + k * c1p + c0;
+                // two 128-bit broadcast reads instead of eight scalar ones (w_s and c1p keep every row 16-byte aligned);
+                // the FMA order is unchanged, so the bits are too
+                const float4 wa = *reinterpret_cast<const float4 *>(w_s + k * c1p + c0);
+                const float4 wb = *reinterpret_cast<const float4 *>(w_s + k * c1p + c0 + 4);
+                const float wk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) p[k] = __fmaf_rn(xf[j], wk[j], p[k]);
             }
@@ -262,11 +266,14 @@ __device__ __forceinline__ void pixel_probs(const __half *__restrict__ x /*c1p h
     }
 }
 
-template <int KMAX>
-__global__ void __launch_bounds__(256)
-out_probs_kernel(const __half *__restrict__ c9, int c1p, const float *__restrict__ w, const float *__restrict__ b,
-                 int K, int act, float *__restrict__ probs, int64_t total_px) {
-    extern __shared__ float osm[];
+// KFIX / C1FIX > 0: class count and padded input width known at compile time (the reference's heads: K = 1, 3, 9, 35 on
+// 16 or 32 channels) -- loops unroll, the `k < K` predicates vanish; 0: run-time values, KMAX bounds the registers
+template <int KMAX, int KFIX, int C1FIX>
+__global__ void __launch_bounds__(256, 2)
+out_probs_kernel(const __half *__restrict__ c9, int c1p_, const float *__restrict__ w, const float *__restrict__ b,
+                 int K_, int act, float *__restrict__ probs, int64_t total_px) {
+    const int K = KFIX > 0 ? KFIX : K_, c1p = C1FIX > 0 ? C1FIX : c1p_;
+    extern __shared__ __align__(16) float osm[];
     float *w_s = osm, *b_s = osm + K * c1p;
     for (int i = threadIdx.x; i < K * c1p; i += blockDim.x) w_s[i] = w[i];
     for (int i = threadIdx.x; i < K; i += blockDim.x) b_s[i] = b[i];
@@ -294,31 +301,39 @@ struct EnsPtrs {
     const float *b[IMK_MAX_MODELS];
 };
 
-template <int KMAX, bool kMulticlass>
-__global__ void __launch_bounds__(256)
-ensemble_im_kernel(EnsPtrs ens, int M, int c1p, int K, int act, float thr, int strict,
+template <int KMAX, bool kMulticlass, int KFIX, int C1FIX>
+__global__ void __launch_bounds__(256, 2)
+ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int strict,
                    int64_t total_px, int64_t HW, int64_t N, int64_t plane_stride,
                    const uint8_t *__restrict__ img, int c, int block_in, int block_out,
                    uint8_t *__restrict__ img_out, uint8_t *__restrict__ labels, uint8_t *__restrict__ im_out,
                    int64_t *__restrict__ im_size, int64_t *__restrict__ pred_size,
                    unsigned long long *__restrict__ presence) {
     // labels: plane k of this launch starts at labels + k * plane_stride; pred_size plane k at pred_size + k * N
-    extern __shared__ float esm[];
-    const int per_model = K * c1p + K;
+    const int K = KFIX > 0 ? KFIX : K_, c1p = C1FIX > 0 ? C1FIX : c1p_;
+    extern __shared__ __align__(16) float esm[];
+    const int per_model = (K * c1p + K + 3) / 4 * 4;             // 16-byte aligned rows for the 128-bit weight reads
     float *w_all = esm;
-    uint8_t *bytes_s = reinterpret_cast<uint8_t *>(esm + ((size_t)M * per_model + 3) / 4 * 4);   // 16-byte aligned [4][256]: label planes, im
+    uint8_t *lab_s = reinterpret_cast<uint8_t *>(esm + (size_t)M * per_model);   // [8 warps][32] class ids (multiclass)
     for (int m = 0; m < M; ++m) {
         for (int i = threadIdx.x; i < K * c1p; i += blockDim.x) w_all[m * per_model + i] = ens.w[m][i];
         for (int i = threadIdx.x; i < K; i += blockDim.x) w_all[m * per_model + K * c1p + i] = ens.b[m][i];
     }
     __syncthreads();
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (total_px + 255) / 256;
     constexpr int NL = kMulticlass ? 1 : 3;
+    // image vector of the warp-local epilogue: lanes < 2c own one 16-byte vector of the warp's 32 pixels
+    const int ig = lane >= c ? 1 : 0, iv = lane - ig * c;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t p0 = tile * 256;
         const int64_t px = p0 + tid;
         const bool live = px < total_px;
+        const int64_t wpx = p0 + warp * 32;                      // first pixel of this warp (total_px % 16 == 0 on this path)
+        // requested before the models are evaluated: the DRAM latency hides behind the arithmetic
+        const bool img_lane = img_out && lane < 2 * c && wpx + 16 * ig < total_px;
+        uint4 pix = make_uint4(0, 0, 0, 0);
+        if (img_lane) pix = ldg_stream(img + (wpx + 16 * ig) * c + 16 * iv);
         uint32_t im_any = 0, im_cnt = 0;
         uint32_t lab[NL];
 #pragma unroll
@@ -372,30 +387,42 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p, int K, int act, float thr, int s
             for (int k = 0; k < NL; ++k)
                 if (k < K) warp_add_stat(pred_size + (int64_t)k * N, n_u, live ? lab[k] : 0u, uniform);
         }
+        // warp-local 128-bit epilogue over the warp's 32 consecutive pixels: ballots give the 0/255 planes, lanes 0-1
+        // store 16 pixels each, lanes < 2c blank the image; no block-wide barrier on the hot path
+        const uint32_t im_mask = __ballot_sync(0xffffffffu, im_any != 0);
+        const bool vec_lane = lane < 2 && wpx + 16 * lane < total_px;
+        auto expand16 = [](uint32_t bits) {                      // 16 bits -> 16 bytes of 0x00 / 0xFF
+            return make_uint4(bytes01_to_ff(bits4_to_bytes01(bits)), bytes01_to_ff(bits4_to_bytes01(bits >> 4)),
+                              bytes01_to_ff(bits4_to_bytes01(bits >> 8)), bytes01_to_ff(bits4_to_bytes01(bits >> 12)));
+        };
         if (kMulticlass) {
-            bytes_s[tid] = (uint8_t)lab[0];
+            lab_s[warp * 32 + lane] = (uint8_t)lab[0];
+            __syncwarp();
+            if (vec_lane) stg_stream(labels + wpx + 16 * lane, *reinterpret_cast<const uint4 *>(lab_s + warp * 32 + 16 * lane));
+            __syncwarp();
         } else {
 #pragma unroll
-            for (int k = 0; k < NL; ++k)
-                if (k < K) bytes_s[k * 256 + tid] = (lab[k] && !(block_out && k < 2 && im_any)) ? 255 : 0;   // head 2 (HeLa position) stays raw
-        }
-        bytes_s[3 * 256 + tid] = im_any ? 255 : 0;
-        __syncthreads();
-        if (tid < 16) {
-            const int64_t vpx = p0 + 16 * tid;
-            if (vpx < total_px) {          // total_px % 16 == 0 on this path
-                const uint4 imv = *reinterpret_cast<const uint4 *>(bytes_s + 3 * 256 + 16 * tid);
-                const int nl = kMulticlass ? 1 : K;
-                for (int k = 0; k < nl; ++k)
-                    stg_stream(labels + (int64_t)k * plane_stride + vpx, *reinterpret_cast<const uint4 *>(bytes_s + k * 256 + 16 * tid));
-                stg_stream(im_out + vpx, imv);
-                if (img_out) {
-                    const uint32_t imw[4] = {imv.x, imv.y, imv.z, imv.w};
-                    blank_image16_any(img, img_out, c, vpx, imw, block_in != 0);
+            for (int k = 0; k < NL; ++k) {
+                if (k < K) {
+                    // head 2 (HeLa position) stays raw: the reference blanks the circle image drawn from it on the host
+                    const uint32_t mk = __ballot_sync(0xffffffffu, lab[k] && !(block_out && k < 2 && im_any));
+                    if (vec_lane) stg_stream(labels + (int64_t)k * plane_stride + wpx + 16 * lane, expand16(mk >> (16 * lane)));
                 }
             }
         }
-        __syncthreads();
+        if (vec_lane) stg_stream(im_out + wpx + 16 * lane, expand16(im_mask >> (16 * lane)));
+        if (img_lane) {
+            const uint4 imv = expand16(block_in ? (im_mask >> (16 * ig)) : 0u);
+            const uint32_t imw[4] = {imv.x, imv.y, imv.z, imv.w};
+            uint4 o;                                             // compile-time channel count: the byte selectors fold to constants
+            switch (c) {
+                case 1: o = blank_vec_sel<1>(pix, imw, 1, iv); break;
+                case 2: o = blank_vec_sel<2>(pix, imw, 2, iv); break;
+                case 3: o = blank_vec_sel<3>(pix, imw, 3, iv); break;
+                default: o = blank_vec_sel<4>(pix, imw, 4, iv); break;
+            }
+            stg_stream(img_out + (wpx + 16 * ig) * c + 16 * iv, o);
+        }
     }
 }
 
@@ -602,11 +629,16 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
     return IMK_OK;       // c9 == lv[0].a
 }
 
+// f(KMAX, KFIX, C1FIX): the reference's heads get compile-time shapes, anything else the run-time path
 template <typename F>
-static int dispatch_kmax(int K, F &&f) {
-    if (K <= 4) return f(std::integral_constant<int, 4>{});
-    if (K <= 16) return f(std::integral_constant<int, 16>{});
-    return f(std::integral_constant<int, 64>{});
+static int dispatch_head(int K, int c1p, F &&f) {
+    using std::integral_constant;
+#define IMK_HEAD(KK, CC) if (K == KK && c1p == CC) return f(integral_constant<int, KK>{}, integral_constant<int, KK>{}, integral_constant<int, CC>{})
+    IMK_HEAD(1, 16); IMK_HEAD(1, 32); IMK_HEAD(3, 16); IMK_HEAD(3, 32); IMK_HEAD(9, 16); IMK_HEAD(9, 32); IMK_HEAD(35, 16); IMK_HEAD(35, 32);
+#undef IMK_HEAD
+    if (K <= 4) return f(integral_constant<int, 4>{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+    if (K <= 16) return f(integral_constant<int, 16>{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+    return f(integral_constant<int, 64>{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
 }
 
 static int launch_out_probs(imk_unet *net, int64_t n, float *probs, cudaStream_t stream) {
@@ -615,11 +647,11 @@ static int launch_out_probs(imk_unet *net, int64_t n, float *probs, cudaStream_t
     const int64_t px = n * d.height * d.width;
     const int K = d.num_outputmasks, c1p = Lo.cin_p;
     const size_t smem = (size_t)(K * c1p + K) * sizeof(float);
-    return dispatch_kmax(K, [&](auto kmax) -> int {
-        constexpr int KM = decltype(kmax)::value;
-        IMK_CUDA(cudaFuncSetAttribute(out_probs_kernel<KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return dispatch_head(K, c1p, [&](auto kmax, auto kfix, auto c1fix) -> int {
+        constexpr int KM = decltype(kmax)::value, KF = decltype(kfix)::value, CF = decltype(c1fix)::value;
+        IMK_CUDA(cudaFuncSetAttribute(out_probs_kernel<KM, KF, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IMK_PROFILE("out_probs", 23, stream);
-        out_probs_kernel<KM><<<grid_1d(px, 256, 4), 256, smem, stream>>>(net->lvl[0].a, c1p, Lo.w_f32, Lo.bias, K, d.act_out, probs, px);
+        out_probs_kernel<KM, KF, CF><<<grid_1d(px, 256, 4), 256, smem, stream>>>(net->lvl[0].a, c1p, Lo.w_f32, Lo.bias, K, d.act_out, probs, px);
         IMK_LAUNCHED();
         return IMK_OK;
     });
@@ -832,15 +864,15 @@ static int check_ensemble(imk_unet_t *const *nets, int M, const char *who) {
     return IMK_OK;
 }
 
-template <int KMAX, bool MC>
+template <int KMAX, bool MC, int KFIX, int C1FIX>
 static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float thr, int strict, int64_t total_px, int64_t HW,
                       int64_t N, int64_t plane_stride, const uint8_t *img, int c, int block_in, int block_out, uint8_t *img_out, uint8_t *labels,
                       uint8_t *im, int64_t *im_size, int64_t *pred_size, unsigned long long *presence, cudaStream_t stream) {
-    const size_t smem = ((size_t)M * (K * c1p + K) + 3) / 4 * 4 * sizeof(float) + 4 * 256;
-    IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)M * ((K * c1p + K + 3) / 4 * 4) * sizeof(float) + 8 * 32;      // weights + bias per model, class-id bytes per warp
+    IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC, KFIX, C1FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_1d(total_px, 256, 4);
     IMK_PROFILE("ensemble_im", -1, stream);
-    ensemble_im_kernel<KMAX, MC><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, total_px, HW, N, plane_stride, img, c,
+    ensemble_im_kernel<KMAX, MC, KFIX, C1FIX><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, total_px, HW, N, plane_stride, img, c,
                                                                block_in, block_out, img_out, labels, im, im_size, pred_size, presence);
     IMK_LAUNCHED();
     return IMK_OK;
@@ -893,16 +925,19 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
         uint8_t *im_c = im + n0 * HW;
         int64_t *im_size_c = im_size + n0;
         const int64_t total_px = n * HW;
-        if (multiclass) {
-            rc = dispatch_kmax(K, [&](auto kmax) -> int {
-                return launch_ens<decltype(kmax)::value, true>(ens, M, c1p, K, d.act_out, 0.f, 1, total_px, HW, N, N * HW, img_c, d.in_channels,
-                                                               block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
-                                                               nullptr, presence ? presence + n0 * M : nullptr, stream);
-            });
-        } else {
-            rc = launch_ens<4, false>(ens, M, c1p, K, d.act_out, thr, strict, total_px, HW, N, N * HW, img_c, d.in_channels, block_in, block_out,
-                                      img_out_c, labels + n0 * HW, im_c, im_size_c, pred_size ? pred_size + n0 : nullptr, nullptr, stream);
-        }
+        rc = dispatch_head(K, c1p, [&](auto kmax, auto kfix, auto c1fix) -> int {
+            constexpr int KM = decltype(kmax)::value, KF = decltype(kfix)::value, CF = decltype(c1fix)::value;
+            if (multiclass)
+                return launch_ens<KM, true, KF, CF>(ens, M, c1p, K, d.act_out, 0.f, 1, total_px, HW, N, N * HW, img_c, d.in_channels,
+                                                    block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
+                                                    nullptr, presence ? presence + n0 * M : nullptr, stream);
+            if constexpr (KM <= 4)                                // binary IM: K = 1 (ISIC) or 3 (HeLa), checked above
+                return launch_ens<KM < 3 ? (KM == 1 ? 1 : 4) : KM, false, KF, CF>(ens, M, c1p, K, d.act_out, thr, strict, total_px, HW, N, N * HW, img_c,
+                                                     d.in_channels, block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
+                                                     pred_size ? pred_size + n0 : nullptr, nullptr, stream);
+            set_error("%s: binary IM with K = %d", who, K);
+            return IMK_EINVAL;
+        });
         if (rc) return rc;
     }
     if (multiclass && lists_equal) {

@@ -29,6 +29,6 @@ for spec in [""] + a.tiles:
         m.forward_device(x)
     prof = _lib.profile_end()
     tot = sum(p["total_ms"] for p in prof) / 3
-    rows = " ".join(f"{p['name']}[{p['tag']}]={1e3 * p['total_ms'] / p['launches']:.1f}" for p in prof if p["name"].startswith("block_"))
+    rows = " ".join(f"{p['name']}[{p['tag']}]={1e3 * p['total_ms'] / p['launches']:.1f}" for p in prof)
     print(f"{spec or 'planner':40s} total {1e3 * tot:8.1f} us | {rows}", flush=True)
     m.close()
