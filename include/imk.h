@@ -58,6 +58,8 @@ const char *imk_last_error(void);
 int64_t     imk_launch_count(void);
 /* Images per internal trunk pass (the workspace of a model is sized for this many; env IMK_CHUNK overrides). */
 int64_t     imk_max_chunk(void);
+/* Change it (1..1024; 0 restores the default).  Workspaces grow on demand; results do not depend on it. */
+int         imk_set_max_chunk(int64_t n);
 /* 1 when a CUDA device is usable from this process, else 0 (never throws). */
 int         imk_device_available(void);
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "imk_last_error": (C.c_char_p, []),
     "imk_launch_count": (_i64, []),
     "imk_max_chunk": (_i64, []),
+    "imk_set_max_chunk": (_i, [_i64]),
     "imk_device_available": (_i, []),
     "imk_profile_begin": (_i, []),
     "imk_profile_end": (_i, [C.POINTER(ProfileEntry), _i, C.POINTER(_i)]),

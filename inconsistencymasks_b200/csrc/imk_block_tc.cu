@@ -278,6 +278,27 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         const int zn = (a.bar_off - a.a0_off) / 16;
         for (int i = tid; i < zn; i += kBtThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
+    if (a.load_kind == 3) {                           // grayscale uint8 images only (fused_block_build)
+        __syncthreads();                              // the table lives inside the region zeroed above
+        {
+            // one finished row of the input block per pixel value: [256][ld_cp] fp16
+            const int KC1 = a.ld_cp >> 3;
+            for (int t = tid; t < 256 * KC1; t += kBtThreads) {
+                const int xv = t / KC1, kc = t - xv * KC1;
+                const float xf = __fdiv_rn((float)xv, 255.0f);
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = kc * 8 + 2 * j;
+                    float v0 = __fmaf_rn(xf, a.fw[0][ch], a.fb[ch]), v1 = __fmaf_rn(xf, a.fw[0][ch + 1], a.fb[ch + 1]);
+                    v0 = fminf(fmaxf(v0, a.flo[ch]), a.fhi[ch]); v1 = fminf(fmaxf(v1, a.flo[ch + 1]), a.fhi[ch + 1]);
+                    const __half2 h = __floats2half2_rn(v0, v1);
+                    o[j] = *reinterpret_cast<const uint32_t *>(&h);
+                }
+                reinterpret_cast<uint4 *>(smem + a.lut_off)[t] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
     if (a.load_kind == 0) {                           // x/255 as fp16 hi + lo (the same arithmetic the float path uses)
         __syncthreads();                              // the table lives inside the region zeroed above
         if (tid < 256) {
@@ -668,6 +689,33 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                         *reinterpret_cast<uint4 *>(buf + ((size_t)Pn + f) * 16) = reinterpret_cast<const uint4 *>(v)[1];
                     }
                 }
+            } else if (a.load_kind == 3) {
+                // input block through the table: a grayscale uint8 pixel selects the finished fp16 row of the 3x3 stage's
+                // operand (zero outside the image: Conv2D 'same' pads the map the 3x3 reads, unet.py:12)
+                const uint8_t *img = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.H * a.W;
+                {
+                    const uint4 *lut4 = reinterpret_cast<const uint4 *>(smem + a.lut_off);
+                    constexpr int PB = 8;                    // positions in flight per thread
+                    for (int f0 = lt; f0 < npos; f0 += PB * NL) {
+                        uint32_t px[PB];
+#pragma unroll
+                        for (int k = 0; k < PB; ++k) {
+                            const int f = f0 + k * NL;
+                            const int r = (int)__umulhi((unsigned)f, a.pitch_magic), c = f - r * a.pitch;
+                            const int y = y0 - 1 + r, x = x0 - 1 + c;
+                            const bool in = f < npos && y >= 0 && y < a.H && x >= 0 && x < a.W;
+                            px[k] = in ? (uint32_t)__ldg(img + (long long)y * a.W + x) : 256u;
+                        }
+#pragma unroll
+                        for (int k = 0; k < PB; ++k) {
+                            const int f = f0 + k * NL;
+                            if (f >= npos) continue;
+                            for (int kc = 0; kc < KC; ++kc)
+                                *reinterpret_cast<uint4 *>(buf + ((size_t)kc * Pn + f) * 16) =
+                                    px[k] != 256u ? lut4[px[k] * KC + kc] : make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                }
             } else if (a.load_kind == 1) {
                 // the haloed tile: one TMA box per 8-channel plane, zero filled outside the image
                 if (first && elect_one()) {
@@ -841,6 +889,7 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
     off += (size_t)g.Pn2 * (a.s3.ksteps * 2) * 16;
     off += ((size_t)th * tw * n3 * 2 + 127) / 128 * 128;
     if (a.load_kind == 0) off += 1024;
+    if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     off += (size_t)kBtNumBars * 8 + 16;
     g.bytes = off;
     return off <= smem_max;
@@ -921,6 +970,7 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     a.a2_off = (int)off; off += (size_t)a.Pn2 * (a.s3.ksteps * 2) * 16;
     a.o_off = (int)off; off += ((size_t)a.Th * a.Tw * a.s3.n * 2 + 127) / 128 * 128;
     a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
+    if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     a.bar_off = (int)off; off += (size_t)kBtNumBars * 8 + 16;        // everything in [a0_off, bar_off) starts zeroed
     fb.smem = off;
     return off <= (size_t)(two ? kBtSmemMax2 : kBtSmemMax);
@@ -986,9 +1036,25 @@ int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W,
         s.par_off = 0;
     };
     a.load_kind = kind; a.in_c = in_c;
-    for (int j = 0; j < (kind == 1 ? 2 : 3); ++j)
+    for (int j = (kind == 3 ? 1 : 0); j < (kind == 1 ? 2 : 3); ++j)
         if (pad_ch(L[j].cout) > 64) return IMK_OK;            // BtArgs::cpar holds 64 channels per stage
-    if (kind == 1) {
+    if (kind == 3) {
+        // grayscale only: for c = 3 the table would be three fp32 partial-sum tables and an FMA chain per channel on the
+        // loader warps, measured slower than the tensor-core input stage of kind 0 (ISIC 2.3 -> 3.0 ms per 1024 images)
+        if (L[0].ks != 1 || L[1].ks != 3 || L[2].ks != 1 || in_c != 1 || pad_ch(L[0].cout) > 32) return IMK_OK;
+        a.has_s1 = 0;
+        stage(a.s2, L[1], false); stage(a.s3, L[2], false);
+        a.ld_cp = pad_ch(L[0].cout);
+        const float inf = INFINITY;
+        for (int ch = 0; ch < 32; ++ch) { for (int c = 0; c < 4; ++c) a.fw[c][ch] = 0.f; a.fb[ch] = 0.f; a.flo[ch] = 0.f; a.fhi[ch] = inf; }
+        for (int co = 0; co < L[0].cout; ++co) {
+            const float sc = L[0].bn_scale ? L[0].bn_scale[co] : 1.f, sh = L[0].bn_shift ? L[0].bn_shift[co] : 0.f;
+            for (int c = 0; c < in_c; ++c) a.fw[c][co] = sc * L[0].hwio[(size_t)c * L[0].cout + co];
+            a.fb[co] = sc * L[0].bias[co] + sh;
+            a.flo[co] = sc > 0.f ? sh : (sc < 0.f ? -inf : sh);
+            a.fhi[co] = sc > 0.f ? inf : sh;
+        }
+    } else if (kind == 1) {
         if (L[0].ks != 3 || L[1].ks != 1) return IMK_OK;
         a.has_s1 = 0;
         stage(a.s2, L[0], false); stage(a.s3, L[1], false);
@@ -1026,7 +1092,7 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
     if (out_pool && !fused_block_can_pool(fb)) { set_error("fused block: the tile cannot carry the 2x2 max-pool"); return IMK_EINVAL; }
     a.n_tiles = (long long)n * a.tiles_x * a.tiles_y;
     if (a.n_tiles <= 0) return IMK_OK;
-    if (a.load_kind != 0) {
+    if (a.load_kind == 1 || a.load_kind == 2) {
         int rc = make_map(&a.tm_in, in, n, a.H, a.W, a.ld_cp, a.pitch, a.Th + 2);
         if (rc) return rc;
     }

@@ -43,6 +43,10 @@ struct BtArgs {
     float cpar[3][64];
     uint32_t clo[3][32], chi[3][32];    // half2 pairs of the clamp bounds, rounded to fp16
     int has_hi[3];                      // some channel of the stage has a finite upper bound (a BN scale <= 0)
+    // load_kind 3 (FRONT, grayscale uint8 images): the input block x/255 -> 1x1 conv + ReLU -> BN (unet.py:4-9) is a
+    // 256-entry table of finished fp16 rows, built in fp32 at kernel start; the loader warps copy rows straight into the
+    // 3x3 stage's operand buffer: v = x/255 * fw[0][ch] + fb[ch], clamped to [flo, fhi] (BN scale folded as for the stages)
+    float fw[4][32], fb[32], flo[32], fhi[32];
     long long *dbg;                     // optional timeline buffer (IMK_BT_TIMELINE=1): [3 roles][16 tiles][8 events] clocks of CTA 0
 };
 
@@ -61,7 +65,8 @@ struct ConvHost {                       // host view of one Conv2D (+BN) while i
     int ks, cin, cout;
 };
 
-// kind: 0 FRONT (in 1x1, conv3, conv1 of level 0), 1 ENC (conv3, conv1), 2 DEC (conv1a, conv3, conv1b).
+// kind: 0 FRONT (in 1x1, conv3, conv1 of level 0), 1 ENC (conv3, conv1), 2 DEC (conv1a, conv3, conv1b),
+//       3 FRONT for uint8 images with the input block computed by the loader (a chain of two).
 // Leaves fb.ok == false (and returns IMK_OK) when the block does not fit the resident-weight design.
 int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned);
 // out_pool (optional, needs fused_block_can_pool): the 2x2 max-pooled map is written next to `out` by the same kernel.

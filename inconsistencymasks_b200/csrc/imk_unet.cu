@@ -475,19 +475,24 @@ static std::vector<PlanItem> make_plan(const imk_unet_desc &d, const int f[5]) {
     return p;
 }
 
+static int64_t g_max_chunk = 0;
+static int64_t default_chunk() {
+    int64_t v = 512;                         // measured (HeLa): 64 -> 35.5k, 128 -> 39.6k, 256 -> 42.5k, 512 -> 43.7k, 1024 -> 44.7k img/s
+    if (const char *e = getenv("IMK_CHUNK"); e && e[0]) v = atoll(e);
+    return v < 1 ? 1 : (v > 1024 ? 1024 : v);
+}
 int64_t max_chunk() {
-    static int64_t v = 0;
-    if (!v) {
-        v = 512;                             // measured (HeLa): 64 -> 35.5k, 128 -> 39.6k, 256 -> 42.5k, 512 -> 43.7k, 1024 -> 44.7k img/s
-        if (const char *e = getenv("IMK_CHUNK"); e && e[0]) v = atoll(e);
-        if (v < 1) v = 1;
-        if (v > 1024) v = 1024;
-    }
-    return v;
+    if (!g_max_chunk) g_max_chunk = default_chunk();
+    return g_max_chunk;
 }
 
 }  // namespace imk
 extern "C" int64_t imk_max_chunk(void) { return imk::max_chunk(); }
+extern "C" int imk_set_max_chunk(int64_t n) {
+    IMK_REQUIRE(n >= 0 && n <= 1024, "imk_set_max_chunk: %lld outside 0..1024", (long long)n);
+    imk::g_max_chunk = n ? n : imk::default_chunk();
+    return IMK_OK;
+}
 namespace imk {
 
 int unet_reserve(imk_unet *net, int64_t n) {
@@ -558,12 +563,14 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
     const __half *x = nullptr;
     // a fused block whose tile is even-sized also writes the 2x2 max-pooled map (the next level's input)
     auto pooled_of = [&](int l) -> __half * { return (l < 3) ? lv[l + 1].b : lv[4].a; };
-    if (fused && net->fb_enc[0].ok) {
+    const bool front_u8 = fused && in_dtype == IMK_IN_U8 && net->fb_front_u8.ok;
+    if (front_u8 || (fused && net->fb_enc[0].ok)) {
         // input block + encoder block 1 in one kernel: image -> lvl0.skip (+ pooled)
-        const bool pf = fused_block_can_pool(net->fb_enc[0]);
+        const FusedBlock &fb = front_u8 ? net->fb_front_u8 : net->fb_enc[0];
+        const bool pf = fused_block_can_pool(fb);
         {
             IMK_PROFILE("block_front", 0, stream);
-            if ((rc = fused_block_launch(net->fb_enc[0], images, nullptr, lv[0].skip, pf ? pooled_of(0) : nullptr, n, d.swap_rb,
+            if ((rc = fused_block_launch(fb, images, nullptr, lv[0].skip, pf ? pooled_of(0) : nullptr, n, d.swap_rb,
                                          in_dtype == IMK_IN_F32, stream))) return rc;
         }
         li = 3;
@@ -758,6 +765,7 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
             if (net->conv[ci].has_bn) { host[ci].bn_scale = host_bn[bi].data(); host[ci].bn_shift = host_bn[bi + 1].data(); bi += 2; }
         if (d.ks == 3) {
             if ((rc = fused_block_build(net->fb_enc[0], 0, &host[0], d.height, d.width, d.in_channels, net->owned))) return fail(rc);
+            if (!getenv("IMK_BT_NO_FRONT_U8") && (rc = fused_block_build(net->fb_front_u8, 3, &host[0], d.height, d.width, d.in_channels, net->owned))) return fail(rc);
             for (int l = 1; l < 5; ++l)
                 if ((rc = fused_block_build(net->fb_enc[l], 1, &host[1 + 2 * l], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
             for (int l = 0; l < 4; ++l)

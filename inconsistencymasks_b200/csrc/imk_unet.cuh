@@ -36,6 +36,7 @@ struct imk_unet {
     int engine = 2;                             // 0 direct, 1 layer-wise tcgen05, 2 block-fused tcgen05 (falls back per block)
     imk::FusedBlock fb_enc[5];                  // [0] = FRONT (in + enc1), [1..3] = enc2..4, [4] = bottleneck (conv3 + conv1, no pool)
     imk::FusedBlock fb_dec[4];                  // decoder block that OUTPUTS level l
+    imk::FusedBlock fb_front_u8;                // FRONT for uint8 images: input block on the loader warps, chain of two (kind 3)
     std::vector<void *> owned;                  // device allocations freed at destroy
     // workspace (grown on demand), for `cap_n` images
     int64_t cap_n = 0;

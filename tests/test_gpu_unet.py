@@ -112,15 +112,25 @@ def test_swap_rb(U):
     same(a, b)
 
 
-def test_batch_chunking_is_invisible(U):
-    """N larger than the internal chunk (64): results equal per-image calls."""
+def test_batch_chunking_is_invisible(U, F):
+    """N larger than the internal trunk chunk: .predict equals per-image calls, and the fused ensemble path gives the
+    same bits whatever the chunk size (64 vs the default)."""
+    from inconsistencymasks_b200 import _lib
     h, w = 16, 16
-    weights = U.init_weights(1, 3, 0.5, seed=2)
     img = np.random.default_rng(2).integers(0, 256, size=(150, h, w, 1), dtype=np.uint8)
-    model = U.B200UNet(h, w, 1, 3, 0.5, "sigmoid", weights)
-    full = model.predict(img)
-    for i in (0, 63, 64, 127, 128, 149):
-        same(model.predict(img[i:i + 1])[0], full[i])
+    models = [U.B200UNet(h, w, 1, 3, 0.5, "sigmoid", U.init_weights(1, 3, 0.5, seed=2 + j)) for j in range(2)]
+    whole = F._run_batch(models, img, "hela", blank_image=img, block_input=True, block_output=True)
+    assert _lib.lib.imk_max_chunk() >= 150
+    try:
+        _lib.check(_lib.lib.imk_set_max_chunk(64))
+        assert _lib.lib.imk_max_chunk() == 64
+        full = models[0].predict(img)
+        for i in (0, 63, 64, 127, 128, 149):
+            same(models[0].predict(img[i:i + 1])[0], full[i])
+        parts = F._run_batch(models, img, "hela", blank_image=img, block_input=True, block_output=True)
+    finally:
+        _lib.check(_lib.lib.imk_set_max_chunk(0))
+    same(parts.labels, whole.labels); same(parts.im, whole.im); same(parts.image, whole.image); same(parts.im_size, whole.im_size)
 
 
 @pytest.mark.parametrize("kind,c,K,alpha,act", [("binary", 3, 1, 0.5, "sigmoid"), ("hela", 1, 3, 1.0, "sigmoid"),
