@@ -224,31 +224,9 @@ struct OutParams {                      // per model, in shared memory: w[K][c1p
     const float *b;                     // device [K]
 };
 
+// sigmoid / softmax of one pixel's logits in place -- the ONE definition shared by every path
 template <int KMAX>
-__device__ __forceinline__ void pixel_probs(const __half *__restrict__ x /*c1p halves of one pixel*/, int c1p,
-                                            const float *__restrict__ w_s, const float *__restrict__ b_s, int K,
-                                            int act, float (&p)[KMAX]) {
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) p[k] = (k < K) ? b_s[k] : 0.f;
-    for (int c0 = 0; c0 < c1p; c0 += 8) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(x + c0);
-        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
-        float xf[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(hv[q]); xf[2 * q] = f.x; xf[2 * q + 1] = f.y; }
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            if (k < K) {
-                // two 128-bit broadcast reads instead of eight scalar ones (w_s and c1p keep every row 16-byte aligned);
-                // the FMA order is unchanged, so the bits are too
-                const float4 wa = *reinterpret_cast<const float4 *>(w_s + k * c1p + c0);
-                const float4 wb = *reinterpret_cast<const float4 *>(w_s + k * c1p + c0 + 4);
-                const float wk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) p[k] = __fmaf_rn(xf[j], wk[j], p[k]);
-            }
-        }
-    }
+__device__ __forceinline__ void pixel_activation(float (&p)[KMAX], int K, int act) {
     if (act == IMK_ACT_SIGMOID) {
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
@@ -266,6 +244,111 @@ __device__ __forceinline__ void pixel_probs(const __half *__restrict__ x /*c1p h
     }
 }
 
+// run-time shapes: one thread = one pixel, sequential FMAs
+template <int KMAX>
+__device__ __forceinline__ void pixel_probs(const __half *__restrict__ x /*c1p halves of one pixel*/, int c1p,
+                                            const float *__restrict__ w_s, const float *__restrict__ b_s, int K,
+                                            int act, float (&p)[KMAX]) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) p[k] = (k < K) ? b_s[k] : 0.f;
+    for (int c0 = 0; c0 < c1p; c0 += 8) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(x + c0);
+        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+        float xf[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(hv[q]); xf[2 * q] = f.x; xf[2 * q + 1] = f.y; }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                const float4 wa = *reinterpret_cast<const float4 *>(w_s + k * c1p + c0);
+                const float4 wb = *reinterpret_cast<const float4 *>(w_s + k * c1p + c0 + 4);
+                const float wk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) p[k] = __fmaf_rn(xf[j], wk[j], p[k]);
+            }
+        }
+    }
+    pixel_activation<KMAX>(p, K, act);
+}
+
+// -----------------------------------------------------------------------------
+//  The reference's heads (K = 1, 3, 9, 35 on 16 / 32 channels) on the tensor cores: the last layer of a warp's 32
+//  pixels is a [32 x C1] x [C1 x K] product, i.e. 2 m-tiles x ceil(K/8) n-tiles of mma.sync.m16n8k16 (fp16 operands,
+//  fp32 accumulation).  The activations ARE fp16; the fp32 weights enter as hi + lo halves (two MMAs into the same
+//  accumulator), which keeps ~22 bits of them.  Pixels go through a per-warp shared-memory tile (ldmatrix on the way
+//  in, one row per lane on the way out), so everything after the logits stays one-thread-per-pixel.  Both the
+//  materialised (.predict) kernel and the fused ensemble kernel use THIS function for these shapes: identical bits.
+// -----------------------------------------------------------------------------
+template <int KFIX, int C1FIX>
+struct HeadMma {
+    static constexpr int NT = (KFIX + 7) / 8;                    // n tiles of 8 classes
+    static constexpr int KS = C1FIX / 16;                        // k steps of 16 channels
+    static constexpr int APITCH = C1FIX * 2 + 16;                // bytes per pixel row of the A tile: 16-byte aligned, ldmatrix conflict-free
+    static constexpr int CP = NT * 8 + 1;                        // floats per pixel row of the C tile (odd: conflict-free row reads)
+    static constexpr int WARP_BYTES = (32 * APITCH + 32 * CP * 4 + 15) / 16 * 16;
+    static constexpr int BFRAG_WORDS = NT * KS * 4 * 32;         // per model: [n tile][k step][b0_hi, b1_hi, b0_lo, b1_lo][lane]
+
+    // operand-B fragments of one model from its fp32 [K][C1] weights (all threads of the CTA)
+    static __device__ __forceinline__ void prepare(const float *__restrict__ w /*[K][C1]*/, uint32_t *__restrict__ bfrag) {
+        for (int idx = threadIdx.x; idx < BFRAG_WORDS; idx += blockDim.x) {
+            const int lane = idx & 31, q = (idx >> 5) & 3, js = idx >> 7, s = js % KS, j = js / KS;
+            const int g = lane >> 2, t = lane & 3;
+            const int col = j * 8 + g, r0 = s * 16 + 2 * t + ((q & 1) ? 8 : 0);
+            float v0 = 0.f, v1 = 0.f;
+            if (col < KFIX) { v0 = w[col * C1FIX + r0]; v1 = w[col * C1FIX + r0 + 1]; }
+            __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            if (q >= 2) { h0 = __float2half_rn(v0 - __half2float(h0)); h1 = __float2half_rn(v1 - __half2float(h1)); }
+            bfrag[idx] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        }
+    }
+
+    // logits of the warp's 32 pixels (lane = pixel; xv = the pixel's C1 halves, zeros for dead lanes): p[k] = b[k] + x . w[k]
+    static __device__ __forceinline__ void logits(const uint4 (&xv)[C1FIX / 8], uint8_t *__restrict__ wsm, const uint32_t *__restrict__ bfrag,
+                                                  const float *__restrict__ bias, float (&p)[KFIX]) {
+        const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+        uint8_t *At = wsm;
+        float *Ct = reinterpret_cast<float *>(wsm + 32 * APITCH);
+#pragma unroll
+        for (int i = 0; i < C1FIX / 8; ++i) *reinterpret_cast<uint4 *>(At + lane * APITCH + 16 * i) = xv[i];
+        __syncwarp();
+        uint32_t a[2][KS][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kb = s * 32 + (lane >> 4) * 16;
+                const uint32_t addr = smem_u32(At + row * APITCH + kb);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(a[mt][s][0]), "=r"(a[mt][s][1]), "=r"(a[mt][s][2]), "=r"(a[mt][s][3]) : "r"(addr));
+            }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            uint32_t b[KS][4];
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) b[s][q] = bfrag[((j * KS + s) * 4 + q) * 32 + lane];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int s = 0; s < KS; ++s)
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl)
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                                     : "r"(a[mt][s][0]), "r"(a[mt][s][1]), "r"(a[mt][s][2]), "r"(a[mt][s][3]), "r"(b[s][2 * hl]), "r"(b[s][2 * hl + 1]));
+                float *c0 = Ct + (mt * 16 + g) * CP + j * 8 + 2 * t;
+                c0[0] = c[0]; c0[1] = c[1]; c0[8 * CP] = c[2]; c0[8 * CP + 1] = c[3];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < KFIX; ++k) p[k] = __fadd_rn(Ct[lane * CP + k], bias[k]);
+        __syncwarp();                                            // the tiles are reused by the next model / pixel batch
+    }
+};
+
 // KFIX / C1FIX > 0: class count and padded input width known at compile time (the reference's heads: K = 1, 3, 9, 35 on
 // 16 or 32 channels) -- loops unroll, the `k < K` predicates vanish; 0: run-time values, KMAX bounds the registers
 template <int KMAX, int KFIX, int C1FIX>
@@ -277,14 +360,37 @@ out_probs_kernel(const __half *__restrict__ c9, int c1p_, const float *__restric
     float *w_s = osm, *b_s = osm + K * c1p;
     for (int i = threadIdx.x; i < K * c1p; i += blockDim.x) w_s[i] = w[i];
     for (int i = threadIdx.x; i < K; i += blockDim.x) b_s[i] = b[i];
-    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < total_px; px += stride) {
-        float p[KMAX];
-        pixel_probs<KMAX>(c9 + px * c1p, c1p, w_s, b_s, K, act, p);
-        float *dst = probs + px * K;
+    if constexpr (KFIX > 0) {
+        using H = HeadMma<KFIX, C1FIX>;
+        uint32_t *bfrag = reinterpret_cast<uint32_t *>(osm + (K * c1p + K + 3) / 4 * 4);
+        uint8_t *wsm = reinterpret_cast<uint8_t *>(bfrag + H::BFRAG_WORDS) + (threadIdx.x >> 5) * H::WARP_BYTES;
+        H::prepare(w, bfrag);
+        __syncthreads();
+        const int64_t rounded = (total_px + 31) / 32 * 32;      // whole warps take part in the MMAs
+        for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < rounded; px += stride) {
+            const bool live = px < total_px;
+            uint4 xv[C1FIX / 8];
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) if (k < K) dst[k] = p[k];
+            for (int i = 0; i < C1FIX / 8; ++i) xv[i] = live ? *reinterpret_cast<const uint4 *>(c9 + px * C1FIX + 8 * i) : make_uint4(0, 0, 0, 0);
+            float p[KFIX];
+            H::logits(xv, wsm, bfrag, b_s, p);
+            if (live) {
+                pixel_activation<KFIX>(p, KFIX, act);
+                float *dst = probs + px * KFIX;
+#pragma unroll
+                for (int k = 0; k < KFIX; ++k) dst[k] = p[k];
+            }
+        }
+    } else {
+        __syncthreads();
+        for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < total_px; px += stride) {
+            float p[KMAX];
+            pixel_probs<KMAX>(c9 + px * c1p, c1p, w_s, b_s, K, act, p);
+            float *dst = probs + px * K;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) if (k < K) dst[k] = p[k];
+        }
     }
 }
 
@@ -319,6 +425,12 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
         for (int i = threadIdx.x; i < K * c1p; i += blockDim.x) w_all[m * per_model + i] = ens.w[m][i];
         for (int i = threadIdx.x; i < K; i += blockDim.x) w_all[m * per_model + K * c1p + i] = ens.b[m][i];
     }
+    // tensor-core head (compile-time shapes): operand-B fragments of every model, one A / C tile pair per warp
+    using H = HeadMma<(KFIX > 0 ? KFIX : 1), (C1FIX > 0 ? C1FIX : 16)>;
+    uint32_t *bfrag = reinterpret_cast<uint32_t *>(lab_s + 256);
+    uint8_t *wsm = reinterpret_cast<uint8_t *>(bfrag + (size_t)M * H::BFRAG_WORDS) + (threadIdx.x >> 5) * H::WARP_BYTES;
+    if constexpr (KFIX > 0)
+        for (int m = 0; m < M; ++m) H::prepare(ens.w[m], bfrag + (size_t)m * H::BFRAG_WORDS);
     __syncthreads();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (total_px + 255) / 256;
@@ -349,9 +461,18 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
         const int64_t n_u = uniform ? n_first : n;
         for (int m = 0; m < M; ++m) {
             int arg = 0;
-            if (live) {
-                float p[KMAX];
+            float p[KMAX];
+            if constexpr (KFIX > 0) {                           // every lane takes part in the MMAs (dead lanes feed zeros)
+                uint4 xv[H::KS * 2];
+#pragma unroll
+                for (int i = 0; i < H::KS * 2; ++i)
+                    xv[i] = live ? *reinterpret_cast<const uint4 *>(ens.c9[m] + px * c1p + 8 * i) : make_uint4(0, 0, 0, 0);
+                H::logits(xv, wsm, bfrag + (size_t)m * H::BFRAG_WORDS, w_all + m * per_model + K * c1p, p);
+                if (live) pixel_activation<KMAX>(p, K, act);
+            } else if (live) {
                 pixel_probs<KMAX>(ens.c9[m] + px * c1p, c1p, w_all + m * per_model, w_all + m * per_model + K * c1p, K, act, p);
+            }
+            if (live) {
                 if (kMulticlass) {
                     float best = p[0];
 #pragma unroll
@@ -653,9 +774,10 @@ static int launch_out_probs(imk_unet *net, int64_t n, float *probs, cudaStream_t
     const ConvLayer &Lo = net->conv.back();
     const int64_t px = n * d.height * d.width;
     const int K = d.num_outputmasks, c1p = Lo.cin_p;
-    const size_t smem = (size_t)(K * c1p + K) * sizeof(float);
     return dispatch_head(K, c1p, [&](auto kmax, auto kfix, auto c1fix) -> int {
         constexpr int KM = decltype(kmax)::value, KF = decltype(kfix)::value, CF = decltype(c1fix)::value;
+        size_t smem = (size_t)((K * c1p + K + 3) / 4 * 4) * sizeof(float);
+        if constexpr (KF > 0) smem += (size_t)HeadMma<KF, CF>::BFRAG_WORDS * 4 + 8 * (size_t)HeadMma<KF, CF>::WARP_BYTES;
         IMK_CUDA(cudaFuncSetAttribute(out_probs_kernel<KM, KF, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IMK_PROFILE("out_probs", 23, stream);
         out_probs_kernel<KM, KF, CF><<<grid_1d(px, 256, 4), 256, smem, stream>>>(net->lvl[0].a, c1p, Lo.w_f32, Lo.bias, K, d.act_out, probs, px);
@@ -876,7 +998,8 @@ template <int KMAX, bool MC, int KFIX, int C1FIX>
 static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float thr, int strict, int64_t total_px, int64_t HW,
                       int64_t N, int64_t plane_stride, const uint8_t *img, int c, int block_in, int block_out, uint8_t *img_out, uint8_t *labels,
                       uint8_t *im, int64_t *im_size, int64_t *pred_size, unsigned long long *presence, cudaStream_t stream) {
-    const size_t smem = (size_t)M * ((K * c1p + K + 3) / 4 * 4) * sizeof(float) + 8 * 32;      // weights + bias per model, class-id bytes per warp
+    size_t smem = (size_t)M * ((K * c1p + K + 3) / 4 * 4) * sizeof(float) + 8 * 32;            // weights + bias per model, class-id bytes per warp
+    if constexpr (KFIX > 0) smem += (size_t)M * HeadMma<KFIX, C1FIX>::BFRAG_WORDS * 4 + 8 * (size_t)HeadMma<KFIX, C1FIX>::WARP_BYTES;
     IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC, KFIX, C1FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_1d(total_px, 256, 4);
     IMK_PROFILE("ensemble_im", -1, stream);
