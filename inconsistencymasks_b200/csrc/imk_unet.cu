@@ -461,6 +461,7 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
         const int64_t n_u = uniform ? n_first : n;
         for (int m = 0; m < M; ++m) {
             int arg = 0;
+            bool fast_arg = false;                              // arg already holds the argmax of the probabilities
             float p[KMAX];
             if constexpr (KFIX > 0) {                           // every lane takes part in the MMAs (dead lanes feed zeros)
                 uint4 xv[H::KS * 2];
@@ -468,15 +469,45 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
                 for (int i = 0; i < H::KS * 2; ++i)
                     xv[i] = live ? *reinterpret_cast<const uint4 *>(ens.c9[m] + px * c1p + 8 * i) : make_uint4(0, 0, 0, 0);
                 H::logits(xv, wsm, bfrag + (size_t)m * H::BFRAG_WORDS, w_all + m * per_model + K * c1p, p);
-                if (live) pixel_activation<KMAX>(p, K, act);
+                if (live) {
+                    if (kMulticlass && act == IMK_ACT_SOFTMAX) {
+                        // argmax of the softmax without its K divisions: p_k = e_k / sum is monotonic in e_k, and two
+                        // numerators more than 2^-22 apart (relative) cannot round to the same quotient, so the first
+                        // maximum of e is the first maximum of p unless another numerator is that close to it (or a
+                        // NaN is around) -- only then the exact probabilities are formed, with pixel_activation's ops
+                        float mx = p[0];
+#pragma unroll
+                        for (int k = 1; k < KMAX; ++k) mx = fmaxf(mx, p[k]);
+                        float sum = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) { p[k] = __expf(__fsub_rn(p[k], mx)); sum = __fadd_rn(sum, p[k]); }
+                        float best = p[0];
+#pragma unroll
+                        for (int k = 1; k < KMAX; ++k) if (p[k] > best) { best = p[k]; arg = k; }
+                        const float lim = best * 0.99999976f;
+                        int close = 0;
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) close += (p[k] >= lim) ? 1 : 0;
+                        fast_arg = close == 1 && sum == sum;
+                        if (!fast_arg) {
+#pragma unroll
+                            for (int k = 0; k < KMAX; ++k) p[k] = __fdiv_rn(p[k], sum);
+                        }
+                    } else {
+                        pixel_activation<KMAX>(p, K, act);
+                    }
+                }
             } else if (live) {
                 pixel_probs<KMAX>(ens.c9[m] + px * c1p, c1p, w_all + m * per_model, w_all + m * per_model + K * c1p, K, act, p);
             }
             if (live) {
                 if (kMulticlass) {
-                    float best = p[0];
+                    if (!fast_arg) {
+                        arg = 0;
+                        float best = p[0];
 #pragma unroll
-                    for (int k = 1; k < KMAX; ++k) if (k < K) argmax_step(p[k], k, best, arg);
+                        for (int k = 1; k < KMAX; ++k) if (k < K) argmax_step(p[k], k, best, arg);
+                    }
                     if (m == 0) a0 = arg; else im_any |= (arg != a0);
                 } else {
 #pragma unroll

@@ -133,6 +133,33 @@ def test_batch_chunking_is_invisible(U, F):
     same(parts.labels, whole.labels); same(parts.im, whole.im); same(parts.image, whole.image); same(parts.im_size, whole.im_size)
 
 
+@pytest.mark.parametrize("K", [9, 35])
+def test_fused_multiclass_ties_and_near_ties(U, F, K):
+    """The fused multiclass path takes the argmax of the softmax numerators and forms the quotients only when two
+    numerators are within 2^-22 of each other: exact ties (zero last layer: every class equal) and near ties (classes
+    that differ by a few ulps of the bias) must still give what np.argmax gives on the .predict probabilities."""
+    h, w, n, c = 32, 32, 3, 3
+    images = np.random.default_rng(K).integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    models = []
+    for j in range(2):
+        wts = [np.array(a, copy=True) for a in U.init_weights(c, K, 1.0, seed=500 + j)]
+        wts[-2][...] = 0.0                                   # last-layer kernel: logits == bias everywhere
+        bias = np.zeros(K, np.float32)
+        if j == 1:                                           # model 1: class 5 above class 2 by one ulp, the rest tied below
+            bias[:] = -1.0
+            bias[2] = 1.0
+            bias[5] = np.nextafter(np.float32(1.0), np.float32(2.0))
+        wts[-1][...] = bias
+        models.append(U.B200UNet(h, w, c, K, 1.0, "softmax", wts))
+    probs = [mdl.predict(images) for mdl in models]
+    r = F._run_batch(models, images, "multiclass", blank_image=images, block_input=True, block_output=True)
+    for i in range(n):
+        lab, im, sz, _ = ref_im.im_prediction_multiclass([p[i] for p in probs], False)
+        img_b, lab_b, _ = ref_im.blank_multiclass(images[i], lab, im)
+        same(r.labels[0, i], lab_b); same(r.im[i], im); same(r.image[i], img_b)
+        assert r.im_size[i] == sz
+
+
 @pytest.mark.parametrize("kind,c,K,alpha,act", [("binary", 3, 1, 0.5, "sigmoid"), ("hela", 1, 3, 1.0, "sigmoid"),
                                                 ("multiclass", 3, 9, 1.0, "softmax"), ("multiclass", 3, 35, 1.0, "softmax")])
 @pytest.mark.parametrize("M", [1, 2, 3])
