@@ -35,6 +35,8 @@ static cudaEvent_t prof_event() {
     return e;
 }
 
+bool profiling_active() { return g_prof_on; }
+
 ProfileScope::ProfileScope(const char *name, int tag, cudaStream_t s) : slot(-1), stream(s) {
     if (!g_prof_on) return;
     ProfRec r{name, tag, prof_event(), prof_event()};

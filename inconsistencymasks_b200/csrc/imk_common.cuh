@@ -43,6 +43,7 @@ struct ProfileScope {
     ProfileScope(const char *name, int tag, cudaStream_t s);
     ~ProfileScope();
 };
+bool profiling_active();                // true between imk_profile_begin and imk_profile_end (this thread)
 #define IMK_PROFILE(name, tag, stream) imk::ProfileScope imk_prof_scope_((name), (tag), (stream))
 
 // Call right after a <<<>>> launch.

@@ -12,6 +12,7 @@
 // Order inside a block is Conv -> ReLU -> BatchNorm (unet.py:6-7, 12-16, 34-41): BN is an
 // affine epilogue AFTER the ReLU and is not folded into the convolution.
 #include <math.h>
+#include <algorithm>
 #include <vector>
 #include "imk_im.cuh"
 #include <stdlib.h>
@@ -1013,6 +1014,34 @@ namespace imk {
 static thread_local unsigned long long *g_presence2 = nullptr;
 static thread_local size_t g_presence2_cap = 0;
 
+// The trunks of different models are independent until the ensemble epilogue: they are issued round-robin to the
+// caller's stream and a few auxiliary streams, so that the tail of one model's persistent kernel (SMs whose CTA has
+// run out of tiles) is filled by the next kernel of another model.  IMK_STREAMS=1 restores the sequential order.
+constexpr int kMaxAux = 3;
+struct AuxStreams {
+    int device = -1, n = 0;
+    cudaStream_t s[kMaxAux] = {};
+    cudaEvent_t fork = nullptr, join[kMaxAux] = {};
+};
+static thread_local AuxStreams g_aux;
+static int aux_streams(int want, AuxStreams **out) {
+    int dev = 0;
+    IMK_CUDA(cudaGetDevice(&dev));
+    AuxStreams &A = g_aux;
+    if (A.device != dev) {                                   // (re)create on this device; the old ones die with their context
+        A = AuxStreams{};
+        A.device = dev;
+        IMK_CUDA(cudaEventCreateWithFlags(&A.fork, cudaEventDisableTiming));
+    }
+    while (A.n < want && A.n < kMaxAux) {
+        IMK_CUDA(cudaStreamCreateWithFlags(&A.s[A.n], cudaStreamNonBlocking));
+        IMK_CUDA(cudaEventCreateWithFlags(&A.join[A.n], cudaEventDisableTiming));
+        ++A.n;
+    }
+    *out = &A;
+    return IMK_OK;
+}
+
 static int check_ensemble(imk_unet_t *const *nets, int M, const char *who) {
     IMK_REQUIRE(nets && M >= 1 && M <= IMK_MAX_MODELS, "%s: M=%d outside 1..%d", who, M, IMK_MAX_MODELS);
     for (int m = 0; m < M; ++m) {
@@ -1072,15 +1101,34 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
         presence = g_presence2;
         IMK_CUDA(cudaMemsetAsync(presence, 0, need, stream));
     }
+    int n_streams = 2;
+    if (const char *v = getenv("IMK_STREAMS"); v && v[0]) n_streams = atoi(v);
+    n_streams = std::max(1, std::min(std::min(n_streams, M), kMaxAux + 1));
+    if (profiling_active()) n_streams = 1;                       // per-kernel times are only meaningful without overlap
+    AuxStreams *aux = nullptr;
+    if (n_streams > 1 && (rc = aux_streams(n_streams - 1, &aux))) return rc;
     for (int64_t n0 = 0; n0 < N; n0 += kMaxChunk) {
         const int64_t n = (N - n0 < kMaxChunk) ? N - n0 : kMaxChunk;
         EnsPtrs ens{};
+        // fork: everything already in the caller's stream (uploads, the previous chunk's epilogue that still reads
+        // the workspaces) precedes the auxiliary streams' work
+        if (aux) {
+            IMK_CUDA(cudaEventRecord(aux->fork, stream));
+            for (int a = 0; a < n_streams - 1; ++a) IMK_CUDA(cudaStreamWaitEvent(aux->s[a], aux->fork, 0));
+        }
         for (int m = 0; m < M; ++m) {
-            if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, n, stream))) return rc;
+            const int lane = m % n_streams;
+            cudaStream_t sm = lane == 0 ? stream : aux->s[lane - 1];
+            if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, n, sm))) return rc;
             ens.c9[m] = nets[m]->lvl[0].a;
             ens.w[m] = nets[m]->conv.back().w_f32;
             ens.b[m] = nets[m]->conv.back().bias;
         }
+        if (aux)                                                 // join before the epilogue
+            for (int a = 0; a < n_streams - 1; ++a) {
+                IMK_CUDA(cudaEventRecord(aux->join[a], aux->s[a]));
+                IMK_CUDA(cudaStreamWaitEvent(stream, aux->join[a], 0));
+            }
         // chunk view: pixel arrays offset by n0*HW, per-image statistics by n0; label planes stay N*HW apart
         const uint8_t *img_c = images_dev + n0 * HW * d.in_channels;
         uint8_t *img_out_c = img_out ? img_out + n0 * HW * d.in_channels : nullptr;
