@@ -410,7 +410,7 @@ struct EnsPtrs {
 
 template <int KMAX, bool kMulticlass, int KFIX, int C1FIX>
 __global__ void __launch_bounds__(256, 2)
-ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int strict,
+ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int strict, float dstar,
                    int64_t total_px, int64_t HW, int64_t N, int64_t plane_stride,
                    const uint8_t *__restrict__ img, int c, int block_in, int block_out,
                    uint8_t *__restrict__ img_out, uint8_t *__restrict__ labels, uint8_t *__restrict__ im_out,
@@ -493,6 +493,15 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
                         if (!fast_arg) {
 #pragma unroll
                             for (int k = 0; k < KMAX; ++k) p[k] = __fdiv_rn(p[k], sum);
+                        }
+                    } else if (!kMulticlass && act == IMK_ACT_SIGMOID && dstar > 0.f) {
+                        // threshold of the sigmoid without its division: RN(1 / d) is monotonic in d = 1 + exp(-z), so
+                        // "p >= thr" (or ">") is exactly "d <= dstar" with dstar found on the host by exact fp32 division;
+                        // the vote is stored as 1.0 / 0.0 so that decide() below sees p >= thr <=> vote
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            const float dk = __fadd_rn(1.0f, __expf(-p[k]));
+                            p[k] = dk <= dstar ? 2.0f : -1.0f;       // any value above / below every threshold in (0, 1)
                         }
                     } else {
                         pixel_activation<KMAX>(p, K, act);
@@ -1062,8 +1071,17 @@ static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float 
     if constexpr (KFIX > 0) smem += (size_t)M * HeadMma<KFIX, C1FIX>::BFRAG_WORDS * 4 + 8 * (size_t)HeadMma<KFIX, C1FIX>::WARP_BYTES;
     IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC, KFIX, C1FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_1d(total_px, 256, 4);
+    // largest d with RN(1 / d) >= thr (> thr when strict): the sigmoid decision becomes one compare (0 = not applicable)
+    float dstar = 0.f;
+    if (!MC && KFIX > 0 && act == IMK_ACT_SIGMOID && thr > 0.f && thr < 1.f) {
+        auto fires = [&](float dd) { const volatile float q = 1.0f / dd; return strict ? q > thr : q >= thr; };
+        float d0 = 1.0f / thr;
+        for (int it = 0; it < 64 && fires(nextafterf(d0, INFINITY)); ++it) d0 = nextafterf(d0, INFINITY);
+        for (int it = 0; it < 64 && !fires(d0); ++it) d0 = nextafterf(d0, 0.f);
+        if (fires(d0) && !fires(nextafterf(d0, INFINITY))) dstar = d0;
+    }
     IMK_PROFILE("ensemble_im", -1, stream);
-    ensemble_im_kernel<KMAX, MC, KFIX, C1FIX><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, total_px, HW, N, plane_stride, img, c,
+    ensemble_im_kernel<KMAX, MC, KFIX, C1FIX><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, dstar, total_px, HW, N, plane_stride, img, c,
                                                                block_in, block_out, img_out, labels, im, im_size, pred_size, presence);
     IMK_LAUNCHED();
     return IMK_OK;

@@ -19,6 +19,13 @@ for k in d["kernels"]: print(k)
 PY
 tail -3 $OUT/bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "ref exit $?"; cat $OUT/bench_reference.json
+# the other BASELINE configs through the fused path (parity-test shapes; throughput for DESIGN.md)
+for cfg in hela isic isic5 suim city city2; do timeout 120 python tools/ensemble_bench.py --config $cfg --images 512 >> $OUT/configs.jsonl 2>> $OUT/configs.err; done
+python - <<PY
+import json
+for l in open("$OUT/configs.jsonl"):
+    d=json.loads(l); print(d["config"], round(d["images_per_s"]), [ (k["kernel"], k["layer"], k["share"]) for k in d["kernels"][:3]])
+PY
 # ncu launch list of the bench command (share of step per kernel)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/ncu_launches.csv python bench.py --steps 2 --warmup 1 --images-per-step 256 --e2e-images 64 --im-images 64 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1; echo "ncu launches exit $?"
 # ncu full: block-fused trunk kernels (one pass of one model) and the fused epilogue / IM kernels
