@@ -133,6 +133,28 @@ def test_batch_chunking_is_invisible(U, F):
     same(parts.labels, whole.labels); same(parts.im, whole.im); same(parts.image, whole.image); same(parts.im_size, whole.im_size)
 
 
+@pytest.mark.parametrize("thr", [0.5, 0.3, 0.7, 0.123456, 0.9999, 1e-6])
+@pytest.mark.parametrize("kind,c,K", [("binary", 3, 1), ("hela", 1, 3)])
+def test_fused_sigmoid_threshold_is_exact(U, F, kind, c, K, thr):
+    """The fused binary path decides `p >= thr` / `p > thr` as `1 + exp(-z) <= d*` with d* searched on the host; it must
+    agree bit for bit with thresholding the .predict probabilities, for any threshold."""
+    h, w, n = 32, 32, 4
+    images = np.random.default_rng(int(thr * 1e6) + K).integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    models = [U.B200UNet(h, w, c, K, 1.0, "sigmoid", U.init_weights(c, K, 1.0, seed=700 + j)) for j in range(2)]
+    probs = [mdl.predict(images) for mdl in models]
+    r = F._run_batch(models, images, kind, threshold=thr, blank_image=images, block_input=True, block_output=True)
+    for i in range(n):
+        if kind == "binary":
+            lab, im, sz, pred = ref_im.im_prediction_binary([p[i] for p in probs], thr)
+            img_b, lab_b, _ = ref_im.blank_binary(images[i], lab, im)
+            same(r.labels[0, i], lab_b); same(r.im[i], im); same(r.image[i], img_b)
+            assert r.im_size[i] == sz and r.pred_size[0, i] == pred
+        else:
+            alive, dead, pos, im, sz = ref_im.im_prediction_hela([p[i] for p in probs], thr)
+            same(r.labels[2, i], pos); same(r.im[i], im)
+            assert r.im_size[i] == sz
+
+
 @pytest.mark.parametrize("K", [9, 35])
 def test_fused_multiclass_ties_and_near_ties(U, F, K):
     """The fused multiclass path takes the argmax of the softmax numerators and forms the quotients only when two
