@@ -187,6 +187,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore its pinned host buffers, first-touch) to the NUMA node its GPU hangs off: at 8 ranks
+    the end-to-end path moves ~18 GB/s per GPU through host memory, and remote-socket buffers cap it."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def run_b200(args, rank, local_rank, world):
     import torch
@@ -195,6 +218,7 @@ def run_b200(args, rank, local_rank, world):
     from inconsistencymasks_b200._lib import lib, check
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -381,7 +405,8 @@ def run_b200(args, rank, local_rank, world):
                 vs_baseline=None, dtype="f16", data="synthetic",
                 config=dict(workload=WORKLOAD, images_per_step_per_gpu=N, parallelism=f"image-sharded x{world}",
                             l2="inputs and activations per step exceed the 126 MB L2 (no flush needed)",
-                            engine=args.engine or "default", mean_im_size=pool.mean_im_size(total_im, total_n)),
+                            engine=args.engine or "default", mean_im_size=pool.mean_im_size(total_im, total_n),
+                            numa_node_rank0=numa_node),
                 e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          images_per_step=Ne, steps=e2e_steps, api="imk_pseudo_label_binary_host (pinned host buffers)"),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, roofline_im=roof_im, cpu_baseline=cpu,
