@@ -133,6 +133,30 @@ def test_batch_chunking_is_invisible(U, F):
     same(parts.labels, whole.labels); same(parts.im, whole.im); same(parts.image, whole.image); same(parts.im_size, whole.im_size)
 
 
+@pytest.mark.parametrize("case", [(256, 256, 1, 3, 1.0, "sigmoid"), (256, 256, 3, 9, 1.0, "softmax")],
+                         ids=["hela256", "suim256a1"])
+def test_steady_state_pipeline_many_tiles_per_cta(U, case):
+    """Enough full-size images that every persistent CTA of the block-fused engine runs many tiles (double-buffered
+    operands, tile-parity barriers, pooling lag in steady state): probabilities of images spread over the batch must
+    match the fp32 oracle, and two passes must give identical bits (no race)."""
+    h, w, c, K, alpha, act = case
+    n = 40
+    rng = np.random.default_rng(h + K)
+    weights = U.init_weights(c, K, alpha, seed=900 + K)
+    images = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    model = U.B200UNet(h, w, c, K, alpha, act, weights)
+    got = model.predict(images)
+    again = model.predict(images)
+    same(got, again)
+    assert np.isfinite(got).all()
+    for i in (0, 17, n - 1):
+        want = ref_unet.forward(images[i:i + 1], weights, act)[0]
+        err = float(np.abs(got[i] - want).max())
+        assert err < 2e-2, f"image {i}: max |p - oracle| = {err}"
+    # a single-image call (one tile per CTA at most) sees the same bits as the image inside the batch
+    same(model.predict(images[17:18])[0], got[17])
+
+
 @pytest.mark.parametrize("thr", [0.5, 0.3, 0.7, 0.123456, 0.9999, 1e-6])
 @pytest.mark.parametrize("kind,c,K", [("binary", 3, 1), ("hela", 1, 3)])
 def test_fused_sigmoid_threshold_is_exact(U, F, kind, c, K, thr):
