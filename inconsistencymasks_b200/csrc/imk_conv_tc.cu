@@ -369,8 +369,7 @@ static int next_pow2_cols(int c) {
 // Chooses the strip height, the weight staging and the residency (1 or 2 CTAs per SM) for a layer with a small
 // cost model (cycles): a CTA loads its strip, streams the weights once while it issues units x M-blocks MMAs, and
 // drains its accumulators; a ring stage whose MMAs take less than the L2 round trip stalls on the weight stream;
-// two co-resident CTAs share the tensor pipe but hide each other's load / epilogue phases.  Returns false if
-// nothing fits.
+// two co-resident CTAs only help against wave quantisation.  Returns false if nothing fits.
 static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &a) {
     a.H = h; a.W = w; a.cin_p = L.cin_p; a.cout_p = L.cout_p;
     a.taps = L.ks * L.ks; a.halo = L.ks / 2; a.pitch = w + 2 * a.halo;
@@ -383,6 +382,8 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
     const double mma_cyc = 64.0 + 0.8 * L.cout_p;
     const double l2_trip = 1500.0;
     double best = -1.0;
+    int force_th = 0;                                            // tuning aid: IMK_TC_TH pins the strip height of 3x3 layers
+    if (const char *v = getenv("IMK_TC_TH"); v && v[0] && L.ks == 3) force_th = atoi(v);
     for (int stage_max = kWStageMax; stage_max >= 8 * 1024; stage_max >>= 1) {
         int U = 1;
         for (int d = 1; d <= a.units_total; ++d)
@@ -394,6 +395,7 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
             const int max_smem = pass == 0 ? 110 * 1024 : 220 * 1024;
             const int resident = pass == 0 ? 2 : 1;
             for (int th = std::min(h, 32); th >= 1; --th) {
+                if (force_th > 0 && th != force_th) continue;
                 const int nmb = (th * a.pitch + 127) / 128;
                 if (nmb > kMaxMBlocks || nmb * L.cout_p > max_cols) continue;
                 const int pn = (nmb * 128 + 2 * a.halo * a.pitch + 2 * a.halo) | 1;
@@ -404,7 +406,11 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
                 const double t_stream = n_stages > 1 ? n_stages * std::max(U * nmb * mma_cyc, l2_trip / (kWSlots - 1)) : t_mma;
                 const double t_io = 1500.0 + act_bytes / 12.0 + nmb * (L.cout_p / 16) * 400.0;   // strip load + epilogue, not overlapped inside a CTA
                 const double t_cta = t_io + std::max(t_mma, t_stream);
-                const double wave = resident == 2 ? std::max(2.0 * t_mma, t_cta) : t_cta;
+                // measured (IMK_TC_TH sweep, r01): two co-resident CTAs do not overlap -- every phase of this kernel is bound
+                // by the SM's shared-memory bandwidth -- so a pair costs a little more than two CTAs back to back
+                // (3x3 layers up to 128 output channels; for the 1x1 layers and the N = 256 bottleneck the pair does overlap)
+                const bool no_overlap = a.taps == 9 && L.cout_p <= 128;
+                const double wave = resident == 2 ? (no_overlap ? 2.2 * t_cta : std::max(2.0 * t_mma, t_cta)) : t_cta;
                 const double waves = std::ceil(ctas / (double)(kNumSMs * resident));
                 const double cost = waves * wave;
                 if (best < 0 || cost < best) {
