@@ -408,8 +408,8 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
                 const double t_cta = t_io + std::max(t_mma, t_stream);
                 // measured (IMK_TC_TH sweep, r01): two co-resident CTAs do not overlap -- every phase of this kernel is bound
                 // by the SM's shared-memory bandwidth -- so a pair costs a little more than two CTAs back to back
-                // (3x3 layers up to 128 output channels; for the 1x1 layers and the N = 256 bottleneck the pair does overlap)
-                const bool no_overlap = a.taps == 9 && L.cout_p <= 128;
+                // (3x3 layers on maps of at least 32x32; for the 1x1 layers and the 16x16 bottleneck the pair does overlap)
+                const bool no_overlap = a.taps == 9 && h * w >= 1024;
                 const double wave = resident == 2 ? (no_overlap ? 2.2 * t_cta : std::max(2.0 * t_mma, t_cta)) : t_cta;
                 const double waves = std::ceil(ctas / (double)(kNumSMs * resident));
                 const double cost = waves * wave;
