@@ -1,37 +1,40 @@
 // Block-fused tcgen05 engine: one persistent, warp-specialised kernel runs a whole U-Net
 // block (unet.py:4-43) per tile without the intermediate maps ever leaving the SM:
 //
-//   FRONT (level 0)  uint8 image -> [x/255 -> 1x1 conv + ReLU + BN]  -> [3x3 conv + ReLU] -> [1x1 conv + ReLU + BN] -> skip
-//   ENC   (level>=1) pooled map  ->                                     [3x3 conv + ReLU] -> [1x1 conv + ReLU + BN] -> skip
+//   FRONT (level 0)  uint8 image -> [x/255 -> 1x1 conv + ReLU + BN]  -> [3x3 conv + ReLU] -> [1x1 conv + ReLU + BN] -> skip (+ pooled)
+//   ENC   (level>=1) pooled map  ->                                     [3x3 conv + ReLU] -> [1x1 conv + ReLU + BN] -> skip (+ pooled)
 //   DEC              up2x(lo) + skip -> [1x1 conv + ReLU + BN]       -> [3x3 conv + ReLU] -> [1x1 conv + ReLU + BN] -> map
 //
-// i.e. a chain of up to three GEMM stages S1 (1x1 over the haloed tile), S2 (3x3), S3 (1x1).
+// i.e. a chain of up to three GEMM stages S1 (1x1 over the haloed tile), S2 (3x3), S3 (1x1).  For grayscale uint8
+// images FRONT is a chain of two: the input block is a 256-entry table of finished rows (load_kind 3).
 // A tile is Th x Tw output pixels of one image.  All operands live in shared memory in the
 // canonical no-swizzle K-major core-matrix layout over the FLAT padded tile index
 // f = row * pitch + col (pitch = Tw + 2):  addr(kc, f) = base + (kc * Pn + f) * 16, so the
 // nine taps of the 3x3 stage are nine descriptor offsets into the same buffer (no im2col) and
 // the output of one stage's epilogue IS the A operand of the next stage.  Accumulators live in
-// TMEM (three regions R1/R2/R3, one per stage); the weights of all stages stay resident in
-// shared memory for the life of the CTA.
+// TMEM (three regions R1/R2/R3, one per stage); the weights of all stages (BN scale folded in) stay
+// resident in shared memory for the life of the CTA.
 //
-// Roles (800 threads, 1 CTA / SM, grid = min(tiles, 148), tiles strided over CTAs):
-//   warps 0-15  epilogue: tcgen05.ld -> +bias, ReLU, BN -> fp16 -> next stage's smem operand / global
-//               (warp w owns TMEM lanes 32*(w%4).., M blocks b = w/4 (mod 4))
+// Roles (block_tc_kernel<16, 8>: 832 threads, 1 CTA / SM, grid = min(tiles, 148), tiles strided over CTAs):
+//   warps 0-15  epilogue: tcgen05.ld (two 16-column loads per wait) -> + b' (fp32) -> fp16 -> clamp on packed halves ->
+//               next stage's smem operand / output staging tile (warp w owns TMEM lanes 32*(w%4).., M blocks w/4 (mod 4))
 //   warp  16    TMEM allocation + tcgen05.mma issue (one elected thread, fully unrolled K steps: a small-N
 //               SS MMA retires every ~39 cycles -- the A operand read, 4 KB at 128 B/clk -- so the issue
 //               sequence must not cost more than that)
-//   warps 17-24 loaders.  ENC / DEC: the haloed tile is ONE TMA box per 8-channel plane
-//               ({8 ch, pitch, Th+2, 1} of the NHWC map lands exactly as a plane of the flat layout, zero
-//               filled outside the image); DEC additionally TMA-loads the half-resolution tile into a
-//               staging area and the loader warps add it in place (nearest-upsample-2x + add, unet.py:32-33).
-//               FRONT: uint8 pixels through a 256-entry x/255 table, split into fp16 hi + lo K slots.
-// The stages of consecutive tiles are software-pipelined so that the epilogue warps never wait for
-// the tensor pipe:
-//   epilogue iteration i :  E1(i)            E3(i-1)          E2(i)
-//   MMA      iteration i :  S2(i)  S1(i+1)                    S3(i)
-//   loader               :  tile i+1 as soon as S1(i) / S2(i) has consumed the buffer
-// All hand-offs are mbarriers (tcgen05.commit on the MMA side, complete_tx on the TMA side); every
-// barrier completes exactly once per tile so the wait parity is the tile parity.
+//   warps 17-24 loaders.  ENC / DEC: the haloed tile is ONE TMA box per 8-channel plane ({8 ch, pitch, Th+2, 1}
+//               of the NHWC map lands exactly as a plane of the flat layout, zero filled outside the image); DEC
+//               fetches the half-resolution tile into registers meanwhile and adds it in place (nearest-upsample-2x
+//               + add, unet.py:32-33).  FRONT: uint8 pixels through a 256-entry table (x/255 split into fp16 hi + lo
+//               K slots, or finished rows for grayscale).  FRONT / ENC: the loader warps also write the 2x2
+//               max-pooled tile (unet.py:18) from the staging buffer between two loads.
+//   warp  25    store: the finished tile leaves the staging buffer as one cp.async.bulk per image row.
+// Schedule.  A1 (S1 output / S2 input; loader output in a chain of two) is double-buffered by tile parity.  The MMA
+// warp issues  S1(i+1), S3(i-1), S2(i)  per iteration; the tensor pipe executes in order, so
+//   * E1(i+1) and E3(i-1) run while S2(i) executes (it reads the OTHER A1 buffer),
+//   * E2(i) follows S2(i) block by block (per-block tcgen05.commit), after S3(i-1) has stopped reading the single A2,
+//   * the loader works one (chain of three) or two (chain of two) tiles ahead.
+// All hand-offs are mbarriers (tcgen05.commit on the MMA side, complete_tx on the TMA side); every barrier completes
+// exactly once per tile (per use of a loader buffer), so the wait parity is the tile (use) parity.
 #include <algorithm>
 #include <type_traits>
 #include <math.h>
