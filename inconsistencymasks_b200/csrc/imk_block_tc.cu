@@ -994,7 +994,7 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 // fp16 NHWC [n, h, w, c] with boxes {8 ch, box_w, box_h, 1}; out-of-bounds elements read as zero
-static int make_map(CUtensorMap *map, const void *base, int64_t n, int h, int w, int c, int box_w, int box_h) {
+int make_map(CUtensorMap *map, const void *base, int64_t n, int h, int w, int c, int box_w, int box_h) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return IMK_ECUDA; }
     const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};

@@ -65,6 +65,9 @@ struct ConvHost {                       // host view of one Conv2D (+BN) while i
     int ks, cin, cout;
 };
 
+// TMA map of an fp16 NHWC map [n, h, w, c] with boxes {8 ch, box_w, box_h, 1}; out-of-bounds elements read as zero
+int make_map(CUtensorMap *map, const void *base, int64_t n, int h, int w, int c, int box_w, int box_h);
+
 // kind: 0 FRONT (in 1x1, conv3, conv1 of level 0), 1 ENC (conv3, conv1), 2 DEC (conv1a, conv3, conv1b),
 //       3 FRONT for uint8 images with the input block computed by the loader (a chain of two).
 // Leaves fb.ok == false (and returns IMK_OK) when the block does not fit the resident-weight design.

@@ -43,6 +43,8 @@ struct TcArgs {
     int units_total, units_per_stage, unit_bytes, ksteps, n_stages;
     int act_bytes, stage_bytes;
     int out_cstride, out_coff;              // channels of the whole output map / first channel of this launch (N split of wide layers)
+    int use_tma;                            // strip load: one TMA box per 8-channel plane (plain layers, pitch <= 256)
+    alignas(64) CUtensorMap tm_in;          // {8 ch, pitch, Th + 2 halo, 1} boxes of the fp16 NHWC input
     long long *dbg;                         // optional timeline of CTA (0,0) (IMK_TC_TIMELINE=1): 8 clock64 stamps
 };
 
@@ -94,8 +96,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c, int x, int y, int n, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(n), "r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(kTcThreads)
-conv_tc_kernel(const TcArgs a) {
+conv_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *act = smem;
     uint8_t *wring = smem + a.act_bytes;
@@ -103,7 +110,8 @@ conv_tc_kernel(const TcArgs a) {
     uint64_t *full = reinterpret_cast<uint64_t *>(par + 3 * a.cout_p);
     uint64_t *empty = full + kWSlots;
     uint64_t *acc_full = empty + kWSlots;                   // [kMaxMBlocks]: accumulators of M block b are final
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + kMaxMBlocks);
+    uint64_t *act_full = acc_full + kMaxMBlocks;            // the TMA boxes of the input strip have landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(act_full + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int strip = blockIdx.x;
@@ -119,7 +127,16 @@ conv_tc_kernel(const TcArgs a) {
     if (warp == 4 && lane == 0) {
         for (int s = 0; s < kWSlots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < kMaxMBlocks; ++b) mbar_init(&acc_full[b], 1);
+        mbar_init(act_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (a.use_tma) {
+            // the whole haloed strip: one box per 8-channel plane, landing exactly as a plane of the flat layout, zero
+            // filled outside the image -- no thread computes an address
+            const int rows_ = a.Th + 2 * a.halo;
+            mbar_expect_tx(act_full, (uint32_t)KC * 16u * (uint32_t)(rows_ * a.pitch));
+            for (int kc = 0; kc < KC; ++kc)
+                tma_load_4d(smem_u32(act) + (uint32_t)(kc * a.Pn) * 16u, &a.tm_in, kc * 8, -a.halo, y0 - a.halo, (int)n, act_full);
+        }
         // weights do not depend on the strip: start streaming them right away
         const int pre = a.n_stages < kWSlots ? a.n_stages : kWSlots;
         for (int s = 0; s < pre; ++s) {
@@ -145,7 +162,10 @@ conv_tc_kernel(const TcArgs a) {
         const unsigned kc_magic = 0xFFFFFFFFu / (unsigned)KC + 1u, pitch_magic = 0xFFFFFFFFu / (unsigned)a.pitch + 1u;   // exact for i < 2^20
         const __half *in_n = a.in + n * (int64_t)a.H * a.W * a.cin_p;
         const __half *lo_n = a.in_lo ? a.in_lo + n * (int64_t)(a.H >> 1) * (a.W >> 1) * a.cin_p : nullptr;
-        if (!lo_n) {
+        if (a.use_tma) {
+            __syncthreads();                                   // act_full is initialised
+            mbar_wait(act_full, 0);
+        } else if (!lo_n) {
             // plain layers: 16-byte cp.async straight into the operand layout (zero-fill outside the
             // image), every item of the strip in flight at once, no register staging
             const uint32_t act_u32 = smem_u32(act);
@@ -370,7 +390,7 @@ static int next_pow2_cols(int c) {
 // cost model (cycles): a CTA loads its strip, streams the weights once while it issues units x M-blocks MMAs, and
 // drains its accumulators; a ring stage whose MMAs take less than the L2 round trip stalls on the weight stream;
 // two co-resident CTAs only help against wave quantisation.  Returns false if nothing fits.
-static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &a) {
+static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, bool tma, TcArgs &a) {
     a.H = h; a.W = w; a.cin_p = L.cin_p; a.cout_p = L.cout_p;
     a.taps = L.ks * L.ks; a.halo = L.ks / 2; a.pitch = w + 2 * a.halo;
     a.ksteps = L.cin_p / 16;
@@ -398,7 +418,10 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, TcArgs &
                 if (force_th > 0 && th != force_th) continue;
                 const int nmb = (th * a.pitch + 127) / 128;
                 if (nmb > kMaxMBlocks || nmb * L.cout_p > max_cols) continue;
-                const int pn = (nmb * 128 + 2 * a.halo * a.pitch + 2 * a.halo) | 1;
+                // plane stride in positions: a multiple of 8 (128-byte aligned TMA destinations) or odd (conflict-free
+                // 16-byte writes of the thread-staged loaders)
+                const int pn0 = nmb * 128 + 2 * a.halo * a.pitch + 2 * a.halo;
+                const int pn = tma ? (std::max(pn0, (th + 2 * a.halo) * a.pitch) + 7) / 8 * 8 : (pn0 | 1);
                 const int act_bytes = (KC * pn * 16 + 127) / 128 * 128;
                 if (act_bytes + fixed > max_smem) continue;
                 const double ctas = (double)((h + th - 1) / th) * (double)std::max<int64_t>(n_images, 1);
@@ -430,7 +453,7 @@ bool conv_tc_fits(const ConvLayer &L, int h, int w) {
     if (!conv_tc_supported(L) || !L.w_umma) return false;
     ConvLayer Lp = L;
     Lp.cout_p = L.cout_p / tc_parts(L);
-    return tc_plan(Lp, h, w, 64, a);
+    return tc_plan(Lp, h, w, 64, false, a);
 }
 
 int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __half *out, __half *pool_out,
@@ -440,10 +463,17 @@ int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __
     ConvLayer Lp = L;
     Lp.cout_p = L.cout_p / parts;
     TcArgs a{};
-    if (!tc_plan(Lp, h, w, n, a)) { set_error("conv_tc_launch: no strip configuration fits (cin_p=%d cout_p=%d %dx%d)", L.cin_p, L.cout_p, h, w); return IMK_ESTATE; }
+    bool tma = !in_lo && w + 2 * (L.ks / 2) <= 256 && !env_flag("IMK_TC_NO_TMA");
+    if (tma && !tc_plan(Lp, h, w, n, true, a)) tma = false;          // the aligned plane stride did not fit: thread-staged load
+    if (!tma && !tc_plan(Lp, h, w, n, false, a)) { set_error("conv_tc_launch: no strip configuration fits (cin_p=%d cout_p=%d %dx%d)", L.cin_p, L.cout_p, h, w); return IMK_ESTATE; }
     a.in = in; a.in_lo = in_lo; a.out = out;
     a.out_cstride = L.cout_p;
-    const size_t smem = (size_t)a.act_bytes + kWSlots * a.stage_bytes + 3 * a.cout_p * 4 + (2 * kWSlots + kMaxMBlocks) * 8 + 16;
+    a.use_tma = tma ? 1 : 0;
+    if (tma) {
+        int rc = make_map(&a.tm_in, in, n, h, w, L.cin_p, a.pitch, a.Th + 2 * a.halo);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)a.act_bytes + kWSlots * a.stage_bytes + 3 * a.cout_p * 4 + (2 * kWSlots + kMaxMBlocks + 1) * 8 + 16;
     static size_t attr_set = 0;
     if (smem > attr_set) {
         IMK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
