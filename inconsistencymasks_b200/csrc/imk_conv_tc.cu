@@ -427,7 +427,9 @@ static bool tc_plan(const ConvLayer &L, int h, int w, int64_t n_images, bool tma
                 const double ctas = (double)((h + th - 1) / th) * (double)std::max<int64_t>(n_images, 1);
                 const double t_mma = a.units_total * nmb * mma_cyc;
                 const double t_stream = n_stages > 1 ? n_stages * std::max(U * nmb * mma_cyc, l2_trip / (kWSlots - 1)) : t_mma;
-                const double t_io = 1500.0 + act_bytes / 12.0 + nmb * (L.cout_p / 16) * 400.0;   // strip load + epilogue, not overlapped inside a CTA
+                // CTA start-up (barriers, TMEM, first weight stage in flight: ~3 us measured on small strips) + strip load +
+                // epilogue, none of them overlapped inside a CTA
+                const double t_io = 6000.0 + act_bytes / 12.0 + nmb * (L.cout_p / 16) * 400.0;
                 const double t_cta = t_io + std::max(t_mma, t_stream);
                 // measured (IMK_TC_TH sweep, r01): two co-resident CTAs do not overlap -- every phase of this kernel is bound
                 // by the SM's shared-memory bandwidth -- so a pair costs a little more than two CTAs back to back
