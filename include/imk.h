@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define IMK_VERSION 100
+#define IMK_VERSION 200
 
 #define IMK_OK        0
 #define IMK_EINVAL   -1   /* bad argument (shape, NULL pointer, unsupported K / M) */
@@ -176,8 +176,8 @@ int  imk_unet_param_count(const imk_unet_t *net, int64_t *count);
  * 0 = shared-memory-tiled direct convolutions everywhere, 1 = tcgen05 implicit GEMM
  * where Cin is wide enough (default).  Both are CUDA; used for A/B measurements. */
 int  imk_unet_set_engine(imk_unet_t *net, int engine);
-/* Changes desc.swap_rb after creation (the same weights serve get_im_prediction_*, which
- * receive the RGB array, and create_pseudo_labels_im_*, which hold the BGR one). */
+/* Changes desc.swap_rb after creation.  The flag belongs to imk_unet_forward / imk_unet_predict_host only;
+ * the ensemble and host-pipeline calls below take their own per-call swap_rb and never touch it. */
 int  imk_unet_set_swap_rb(imk_unet_t *net, int swap_rb);
 
 /* probs_dev float32 [N,H,W,K].  images_dev: uint8 or float32 [N,H,W,c] per in_dtype. */
@@ -192,12 +192,15 @@ int imk_unet_predict_host(imk_unet_t *net, const void *images_host, int in_dtype
  *  probability maps never written to HBM.  Same outputs as imk_im_binary /
  *  imk_im_multiclass fed with imk_unet_forward's probabilities, bit for bit.
  *  All models must share height, width, in_channels, num_outputmasks, act_out.
+ *  swap_rb (per call, in_channels == 3): 1 = the models are fed channel 2-i of images_dev,
+ *  i.e. cv2.cvtColor(image, COLOR_BGR2RGB) of functions.py:2847-2852, while img_out keeps the
+ *  buffer's own (BGR) order like the array the reference blanks (functions.py:2867-2874).
  * ------------------------------------------------------------------------- */
-int imk_ensemble_im_binary(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+int imk_ensemble_im_binary(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N, int swap_rb,
                            float thr, int strict_gt, int block_in, int block_out,
                            uint8_t *img_out_dev, uint8_t *labels_dev, uint8_t *im_dev,
                            int64_t *im_size_dev, int64_t *pred_size_dev, void *stream);
-int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N, int swap_rb,
                                int block_in, int block_out,
                                uint8_t *img_out_dev, uint8_t *label_dev, uint8_t *im_dev,
                                int64_t *im_size_dev, uint8_t *lists_equal_dev, void *stream);
@@ -210,11 +213,11 @@ int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *im
  *  dilate_kernel == 0 only (the config.ini defaults); use the device-buffer calls
  *  for morphology.  Outputs as in the device calls above; any output may be NULL.
  * ------------------------------------------------------------------------- */
-int imk_pseudo_label_binary_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+int imk_pseudo_label_binary_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
                                  float thr, int strict_gt, int block_in, int block_out,
                                  uint8_t *img_out_host, uint8_t *labels_host, uint8_t *im_host,
                                  int64_t *im_size_host, int64_t *pred_size_host, int64_t chunk);
-int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
                                      int block_in, int block_out,
                                      uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_host,
                                      int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk);

@@ -53,10 +53,10 @@ SIGNATURES = {
     "imk_unet_set_swap_rb": (_i, [_vp, _i]),
     "imk_unet_forward": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "imk_unet_predict_host": (_i, [_vp, _vp, _i, _i64, _vp]),
-    "imk_ensemble_im_binary": (_i, [_vp, _i, _vp, _i64, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "imk_ensemble_im_multiclass": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "imk_pseudo_label_binary_host": (_i, [_vp, _i, _vp, _i64, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
-    "imk_pseudo_label_multiclass_host": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "imk_ensemble_im_binary": (_i, [_vp, _i, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "imk_ensemble_im_multiclass": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "imk_pseudo_label_binary_host": (_i, [_vp, _i, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "imk_pseudo_label_multiclass_host": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
 }
 
 

@@ -174,7 +174,7 @@ int pipeline_reserve(Pipeline &P, int64_t chunk, size_t img_bytes, size_t px_byt
     return IMK_OK;
 }
 
-int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images, int64_t N,
+int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images, int64_t N, int swap_rb,
                       float thr, int strict, int block_in, int block_out,
                       uint8_t *img_out, uint8_t *labels, uint8_t *im, int64_t *im_size, int64_t *pred_size,
                       uint8_t *lists_equal, int64_t chunk, const char *who) {
@@ -204,10 +204,10 @@ int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uin
         IMK_CUDA(cudaStreamWaitEvent(P.compute, S.up_done, 0));
         if (i >= kSlots) IMK_CUDA(cudaStreamWaitEvent(P.compute, S.down_done, 0));
         if (multiclass)
-            rc = imk_ensemble_im_multiclass(nets, M, S.img, n, block_in, block_out, img_out ? S.img_out : nullptr, S.labels, S.im,
+            rc = imk_ensemble_im_multiclass(nets, M, S.img, n, swap_rb, block_in, block_out, img_out ? S.img_out : nullptr, S.labels, S.im,
                                             S.im_size, lists_equal ? S.lists_equal : nullptr, P.compute);
         else
-            rc = imk_ensemble_im_binary(nets, M, S.img, n, thr, strict, block_in, block_out, img_out ? S.img_out : nullptr, S.labels,
+            rc = imk_ensemble_im_binary(nets, M, S.img, n, swap_rb, thr, strict, block_in, block_out, img_out ? S.img_out : nullptr, S.labels,
                                         S.im, S.im_size, pred_size ? S.pred_size : nullptr, P.compute);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         IMK_CUDA(cudaEventRecord(S.comp_done, P.compute));
@@ -231,18 +231,18 @@ int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uin
 
 }  // namespace
 
-extern "C" int imk_pseudo_label_binary_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+extern "C" int imk_pseudo_label_binary_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
                                             float thr, int strict_gt, int block_in, int block_out,
                                             uint8_t *img_out_host, uint8_t *labels_host, uint8_t *im_host,
                                             int64_t *im_size_host, int64_t *pred_size_host, int64_t chunk) {
-    return run_host_pipeline(nets, M, false, images_host, N, thr, strict_gt, block_in, block_out, img_out_host, labels_host,
+    return run_host_pipeline(nets, M, false, images_host, N, swap_rb, thr, strict_gt, block_in, block_out, img_out_host, labels_host,
                              im_host, im_size_host, pred_size_host, nullptr, chunk, "imk_pseudo_label_binary_host");
 }
 
-extern "C" int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N,
+extern "C" int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
                                                 int block_in, int block_out,
                                                 uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_host,
                                                 int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk) {
-    return run_host_pipeline(nets, M, true, images_host, N, 0.f, 1, block_in, block_out, img_out_host, label_host, im_host,
+    return run_host_pipeline(nets, M, true, images_host, N, swap_rb, 0.f, 1, block_in, block_out, img_out_host, label_host, im_host,
                              im_size_host, nullptr, lists_equal_host, chunk, "imk_pseudo_label_multiclass_host");
 }

@@ -705,7 +705,7 @@ static int launch_conv(imk_unet *net, int layer, const __half *in, const __half 
     return IMK_OK;
 }
 
-int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaStream_t stream) {
+int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int64_t n, cudaStream_t stream) {
     int rc = unet_reserve(net, n);
     if (rc) return rc;
     const imk_unet_desc &d = net->desc;
@@ -732,7 +732,7 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
         const bool pf = fused_block_can_pool(fb);
         {
             IMK_PROFILE("block_front", 0, stream);
-            if ((rc = fused_block_launch(fb, images, nullptr, lv[0].skip, pf ? pooled_of(0) : nullptr, n, d.swap_rb,
+            if ((rc = fused_block_launch(fb, images, nullptr, lv[0].skip, pf ? pooled_of(0) : nullptr, n, swap_rb,
                                          in_dtype == IMK_IN_F32, stream))) return rc;
         }
         li = 3;
@@ -743,10 +743,10 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaS
             const int grid = grid_1d(px0 * (c0.cout_p / 8));
             IMK_PROFILE("in_conv", 0, stream);
             if (in_dtype == IMK_IN_U8)
-                in_conv_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
+                in_conv_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)images, d.in_channels, swap_rb, c0.w_f32, c0.cout,
                                                                    c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
             else
-                in_conv_kernel<float><<<grid, 256, 0, stream>>>((const float *)images, d.in_channels, d.swap_rb, c0.w_f32, c0.cout,
+                in_conv_kernel<float><<<grid, 256, 0, stream>>>((const float *)images, d.in_channels, swap_rb, c0.w_f32, c0.cout,
                                                                  c0.bias, c0.bn_scale, c0.bn_shift, lv[0].b, c0.cout_p, px0);
             IMK_LAUNCHED();
         }
@@ -977,7 +977,7 @@ extern "C" int imk_unet_forward(imk_unet_t *net, const void *images_dev, int in_
     const int64_t HW = (int64_t)d.height * d.width;
     for (int64_t n0 = 0; n0 < N; n0 += kMaxChunk) {
         const int64_t n = (N - n0 < kMaxChunk) ? N - n0 : kMaxChunk;
-        int rc = unet_trunk(net, (const char *)images_dev + n0 * HW * in_px_bytes, in_dtype, n, stream);
+        int rc = unet_trunk(net, (const char *)images_dev + n0 * HW * in_px_bytes, in_dtype, d.swap_rb, n, stream);
         if (rc) return rc;
         if ((rc = launch_out_probs(net, n, probs_dev + n0 * HW * d.num_outputmasks, stream))) return rc;
     }
@@ -1088,7 +1088,7 @@ static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float 
 }
 }  // namespace imk
 
-static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images_dev, int64_t N,
+static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images_dev, int64_t N, int swap_rb,
                         float thr, int strict, int block_in, int block_out,
                         uint8_t *img_out, uint8_t *labels, uint8_t *im, int64_t *im_size, int64_t *pred_size,
                         uint8_t *lists_equal, cudaStream_t stream, const char *who) {
@@ -1137,7 +1137,7 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
         for (int m = 0; m < M; ++m) {
             const int lane = m % n_streams;
             cudaStream_t sm = lane == 0 ? stream : aux->s[lane - 1];
-            if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, n, sm))) return rc;
+            if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, swap_rb ? 1 : 0, n, sm))) return rc;
             ens.c9[m] = nets[m]->lvl[0].a;
             ens.w[m] = nets[m]->conv.back().w_f32;
             ens.b[m] = nets[m]->conv.back().bias;
@@ -1175,18 +1175,18 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
     return IMK_OK;
 }
 
-extern "C" int imk_ensemble_im_binary(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+extern "C" int imk_ensemble_im_binary(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N, int swap_rb,
                                       float thr, int strict_gt, int block_in, int block_out,
                                       uint8_t *img_out_dev, uint8_t *labels_dev, uint8_t *im_dev,
                                       int64_t *im_size_dev, int64_t *pred_size_dev, void *stream) {
-    return ensemble_run(nets, M, false, images_dev, N, thr, strict_gt, block_in, block_out, img_out_dev, labels_dev, im_dev,
+    return ensemble_run(nets, M, false, images_dev, N, swap_rb, thr, strict_gt, block_in, block_out, img_out_dev, labels_dev, im_dev,
                         im_size_dev, pred_size_dev, nullptr, (cudaStream_t)stream, "imk_ensemble_im_binary");
 }
 
-extern "C" int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N,
+extern "C" int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *images_dev, int64_t N, int swap_rb,
                                           int block_in, int block_out,
                                           uint8_t *img_out_dev, uint8_t *label_dev, uint8_t *im_dev,
                                           int64_t *im_size_dev, uint8_t *lists_equal_dev, void *stream) {
-    return ensemble_run(nets, M, true, images_dev, N, 0.f, 1, block_in, block_out, img_out_dev, label_dev, im_dev,
+    return ensemble_run(nets, M, true, images_dev, N, swap_rb, 0.f, 1, block_in, block_out, img_out_dev, label_dev, im_dev,
                         im_size_dev, nullptr, lists_equal_dev, (cudaStream_t)stream, "imk_ensemble_im_multiclass");
 }

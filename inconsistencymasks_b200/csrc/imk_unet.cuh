@@ -53,7 +53,7 @@ namespace imk {
 
 // Runs the 23 hidden layers for images [n0, n0+n) and leaves c9 (decoder level-0
 // output, fp16 [n,H,W,C1p]) in net->lvl[0].a.  `images` points at image n0.
-int unet_trunk(imk_unet *net, const void *images, int in_dtype, int64_t n, cudaStream_t stream);
+int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int64_t n, cudaStream_t stream);
 int unet_reserve(imk_unet *net, int64_t n);
 int64_t max_chunk();                    // images per trunk pass (bounds the workspace; IMK_CHUNK overrides the default)
 #define kMaxChunk (imk::max_chunk())

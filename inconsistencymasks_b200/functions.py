@@ -26,7 +26,20 @@ from . import _lib
 from ._lib import lib, check
 from .unet import B200UNet
 
-THRESHOLD = 0.5          # config.ini:13 -> functions.py:31
+def _config_threshold(default=0.5):
+    """functions.py:25-31 reads ``THRESHOLD`` from ``config.ini`` in the working directory (DEFAULT section,
+    config.ini:13); the same file is honoured here when present, else the reference's shipped value 0.5."""
+    try:
+        import configparser
+        cp = configparser.ConfigParser()
+        if cp.read("config.ini") and cp.has_option("DEFAULT", "THRESHOLD"):
+            return cp.getfloat("DEFAULT", "THRESHOLD")
+    except Exception:
+        pass
+    return default
+
+
+THRESHOLD = _config_threshold()
 
 __all__ = [
     "pred_masks_to_im_binary", "pred_masks_to_im_multiclass", "dilate_mask",
@@ -98,15 +111,23 @@ def pred_masks_to_im_multiclass(pred_masks):
     return label, im, im_size
 
 
-def dilate_mask(mask, kernel_size=3):
-    """functions.py:3075-3100: per-class 3x3 dilation, larger class ids overwrite -> 3x3 max filter."""
+def dilate_mask(mask, kernel_size=3, iterations=1):
+    """functions.py:3075-3100: per-class k x k dilation in ascending class id, later ids overwrite -- i.e. a k x k
+    max filter per iteration (every pixel ends up with the largest class id its window holds).  Returns the input's
+    dtype like the reference (``np.zeros_like(mask)``); class ids must fit uint8 (K <= 35 in config.ini)."""
     torch = _torch()
-    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    mask = np.asarray(mask)
+    if mask.ndim != 2:
+        raise ValueError(f"dilate_mask expects a 2-D class-id map, got shape {mask.shape}")
+    if mask.size and (mask.min() < 0 or mask.max() > 255):
+        raise ValueError("dilate_mask: class ids outside 0..255")
     h, w = mask.shape
-    src = _dev(mask)
+    src = _dev(mask.astype(np.uint8))
     dst = torch.empty_like(src)
-    check(lib.imk_dilate_u8(src.data_ptr(), dst.data_ptr(), 1, h, w, int(kernel_size), _stream()))
-    return dst.cpu().numpy()
+    for _ in range(int(iterations)):
+        check(lib.imk_dilate_u8(src.data_ptr(), dst.data_ptr(), 1, h, w, int(kernel_size), _stream()))
+        src, dst = dst, src
+    return src.cpu().numpy().astype(mask.dtype, copy=False)
 
 
 # ------------------------------------------------------------------ batched device core
@@ -148,8 +169,6 @@ def _run_batch(models, model_input, kind, *, threshold=THRESHOLD, blank_image=No
 
     if fused and not morph:
         # host pipeline: uploads / downloads overlapped with compute inside libimk
-        for mdl in models:
-            mdl.set_swap_rb(swap_rb)
         src = np.ascontiguousarray(model_input)
         labels = np.empty((planes, n, h, w), np.uint8)
         im = np.empty((n, h, w), np.uint8)
@@ -158,14 +177,14 @@ def _run_batch(models, model_input, kind, *, threshold=THRESHOLD, blank_image=No
         hs = _handles(models)
         if kind == "multiclass":
             leq = np.empty(n, np.uint8) if want_lists_equal else None
-            check(lib.imk_pseudo_label_multiclass_host(hs, len(models), src.ctypes.data, n, k_bi, k_bo,
+            check(lib.imk_pseudo_label_multiclass_host(hs, len(models), src.ctypes.data, n, int(swap_rb), k_bi, k_bo,
                                                        img_out.ctypes.data if want_img else None,
                                                        labels.ctypes.data, im.ctypes.data, im_size.ctypes.data,
                                                        leq.ctypes.data if leq is not None else None, 0))
             res.pred_size, res.lists_equal = None, leq
         else:
             pred = np.empty((planes, n), np.int64)
-            check(lib.imk_pseudo_label_binary_host(hs, len(models), src.ctypes.data, n, float(threshold), strict, k_bi, k_bo,
+            check(lib.imk_pseudo_label_binary_host(hs, len(models), src.ctypes.data, n, int(swap_rb), float(threshold), strict, k_bi, k_bo,
                                                    img_out.ctypes.data if want_img else None,
                                                    labels.ctypes.data, im.ctypes.data, im_size.ctypes.data,
                                                    pred.ctypes.data, 0))
@@ -184,14 +203,12 @@ def _run_batch(models, model_input, kind, *, threshold=THRESHOLD, blank_image=No
     d_img_out = torch.empty_like(d_img) if want_img else None
     out_ptr = d_img_out.data_ptr() if want_img else None
     if fused:
-        for mdl in models:
-            mdl.set_swap_rb(swap_rb)
         if kind == "multiclass":
-            check(lib.imk_ensemble_im_multiclass(_handles(models), len(models), d_img.data_ptr(), n, k_bi, k_bo, out_ptr,
+            check(lib.imk_ensemble_im_multiclass(_handles(models), len(models), d_img.data_ptr(), n, int(swap_rb), k_bi, k_bo, out_ptr,
                                                  d_labels.data_ptr(), d_im.data_ptr(), d_im_size.data_ptr(),
                                                  d_leq.data_ptr() if d_leq is not None else None, s))
         else:
-            check(lib.imk_ensemble_im_binary(_handles(models), len(models), d_img.data_ptr(), n, float(threshold), strict,
+            check(lib.imk_ensemble_im_binary(_handles(models), len(models), d_img.data_ptr(), n, int(swap_rb), float(threshold), strict,
                                              k_bi, k_bo, out_ptr, d_labels.data_ptr(), d_im.data_ptr(),
                                              d_im_size.data_ptr(), d_pred.data_ptr(), s))
     else:

@@ -35,7 +35,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.lib.imk_version() == 100
+    assert lib.lib.imk_version() == 200
     assert isinstance(lib.lib.imk_last_error(), bytes)
 
 

@@ -1,0 +1,167 @@
+"""GPU parity at the BASELINE.json shapes, full size:
+
+    isic2 / isic5   256x256x3, alpha 0.5, K=1 sigmoid, M = 2 / 5        (configs[0] / configs[4])
+    hela            256x256x1, alpha 1,   K=3 sigmoid, M = 2            (configs[1])
+    suim            256x256x3, alpha 2,   K=9 softmax, M = 2            (configs[2])
+    city / city2    208x416x3, alpha 1/2, K=35 softmax, M = 2           (configs[3])
+
+Two checks per config:
+  * `.predict` against the fp32 CPU oracle (oracle/ref_unet.py) within the STATED tolerance below, with the
+    max / mean / 99.9th-percentile error and the decision-flip rate appended to gpurun_out/parity_table.jsonl
+    (committed as profiles/parity_table.json);
+  * the fused ensemble path (imk_pseudo_label_*_host, no fp32 map in HBM) against the reference's NumPy IM
+    arithmetic on the `.predict` probabilities of the same models: bit-exact labels, IM, blanked image, sizes.
+The alpha = 2 networks take code paths the alpha <= 1 ones never touch (N-split bottleneck, layer-wise engine for the
+>= 128-channel blocks, single-A1 schedule of the 64-channel decoder), hence the full-size cases.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import ref_im, ref_unet  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# Stated tolerances (fp16 activations with fp32 accumulation vs the fp32 oracle).  One fp16 rounding per layer output
+# (relative 2^-11) through 24 layers leaves a logit error whose TAIL over ~10^5..10^6 pixels reaches ~4e-2, i.e.
+# |dp| ~ 1e-2 near p = 0.5: BASELINE.md's 5e-3 starting figure is met by the 99.9th percentile, not by the maximum
+# (the reference itself runs mixed_float16, so TensorFlow's own fp16 path sits at the same distance from fp32).
+PROB_ATOL_MAX = 1.6e-2
+PROB_ATOL_P999 = 5e-3
+PROB_ATOL_MEAN = 1e-3
+FLIP_RATE_MAX = 5e-3
+
+CONFIGS = {
+    # name: H, W, c, K, alpha, act, M, kind, seed
+    "isic2": (256, 256, 3, 1, 0.5, "sigmoid", 2, "binary", 1),
+    "hela": (256, 256, 1, 3, 1.0, "sigmoid", 2, "hela", 2),
+    "suim": (256, 256, 3, 9, 2.0, "softmax", 2, "multiclass", 3),
+    "city": (208, 416, 3, 35, 1.0, "softmax", 2, "multiclass", 4),
+    "city2": (208, 416, 3, 35, 2.0, "softmax", 2, "multiclass", 4),
+    "isic5": (256, 256, 3, 1, 0.5, "sigmoid", 5, "binary", 5),
+}
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from inconsistencymasks_b200 import unet
+    return unet
+
+
+@pytest.fixture(scope="module")
+def F():
+    from inconsistencymasks_b200 import functions
+    return functions
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.dtype == b.dtype and a.shape == b.shape, (a.dtype, b.dtype, a.shape, b.shape)
+    np.testing.assert_array_equal(a, b)
+
+
+def record(row):
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_table.jsonl"), "a") as f:
+            f.write(json.dumps(row) + "\n")
+    except OSError:
+        pass
+
+
+def build(U, name):
+    h, w, c, K, alpha, act, M, kind, seed = CONFIGS[name]
+    weights = [U.init_weights(c, K, alpha, seed=seed + j) for j in range(M)]
+    models = [U.B200UNet(h, w, c, K, alpha, act, wts) for wts in weights]
+    return weights, models
+
+
+@pytest.mark.parametrize("engine", ["fused", "tcgen05"])
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_predict_full_size_vs_fp32_oracle(U, name, engine):
+    h, w, c, K, alpha, act, M, kind, seed = CONFIGS[name]
+    if engine == "tcgen05" and name in ("isic2", "city"):
+        pytest.skip("layer-wise engine is covered at this width by isic5 / hela")
+    n = 3
+    rng = np.random.default_rng(100 + seed)
+    images = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    weights = U.init_weights(c, K, alpha, seed=seed)
+    model = U.B200UNet(h, w, c, K, alpha, act, weights)
+    model.set_engine(engine)
+    got = model.predict(images)
+    want = ref_unet.forward(images, weights, act)
+    assert got.dtype == np.float32 and got.shape == want.shape and np.isfinite(got).all()
+    err = np.abs(got - want)
+    if act == "softmax":
+        np.testing.assert_allclose(got.sum(-1), 1.0, atol=1e-5)
+        flips = float((got.argmax(-1) != want.argmax(-1)).mean())
+    else:
+        flips = float(((got > 0.5) != (want > 0.5)).mean())
+    row = dict(test="predict_vs_fp32_oracle", config=name, engine=engine, shape=[n, h, w, c], K=K, alpha=alpha,
+               max_abs=float(err.max()), mean_abs=float(err.mean()), p999_abs=float(np.quantile(err, 0.999)), flip_rate=flips)
+    record(row)
+    print("\n", row)
+    assert err.max() <= PROB_ATOL_MAX and err.mean() <= PROB_ATOL_MEAN and row["p999_abs"] <= PROB_ATOL_P999
+    assert flips <= FLIP_RATE_MAX
+    model.close()
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_fused_ensemble_full_size_equals_predict_then_im(U, F, name):
+    h, w, c, K, alpha, act, M, kind, seed = CONFIGS[name]
+    n = 6
+    rng = np.random.default_rng(200 + seed)
+    images = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    weights, models = build(U, name)
+    probs = [mdl.predict(images) for mdl in models]
+    r = F._run_batch(models, images, kind, blank_image=images, block_input=True, block_output=True,
+                     want_lists_equal=(kind == "multiclass"))
+    im_px = 0
+    for i in range(n):
+        if kind == "binary":
+            lab, im, sz, pred = ref_im.im_prediction_binary([p[i] for p in probs], 0.5)
+            img_b, lab_b, _ = ref_im.blank_binary(images[i], lab, im)
+            same(r.labels[0, i], lab_b); same(r.im[i], im); same(r.image[i], img_b)
+            assert r.im_size[i] == sz and r.pred_size[0, i] == pred
+        elif kind == "hela":
+            alive, dead, pos, im, sz = ref_im.im_prediction_hela([p[i] for p in probs])
+            bf, alive_b, dead_b, _, _ = ref_im.blank_hela(images[i, ..., 0], alive, dead, np.zeros((h, w, 3), np.uint8), im)
+            same(r.labels[0, i], alive_b); same(r.labels[1, i], dead_b); same(r.labels[2, i], pos)
+            same(r.im[i], im); same(r.image[i, ..., 0], bf)
+            assert r.im_size[i] == sz
+        else:
+            lab, im, sz, eq = ref_im.im_prediction_multiclass([p[i] for p in probs], True)
+            img_b, lab_b, _ = ref_im.blank_multiclass(images[i], lab, im)
+            same(r.labels[0, i], lab_b); same(r.im[i], im); same(r.image[i], img_b)
+            assert r.im_size[i] == sz and bool(r.lists_equal[i]) == bool(eq)
+        im_px += int((r.im[i] > 0).sum())
+    record(dict(test="fused_equals_predict_then_im", config=name, images=n, M=M, bit_exact=True, im_fraction=im_px / (n * h * w)))
+    for mdl in models:
+        mdl.close()
+
+
+def test_predict_unchanged_by_create_pseudo_labels(U, F, tmp_path):
+    """the BGR->RGB swap of create_pseudo_labels_im_*(rgb=True) is a per-call argument of the C ABI and must
+    not leak into later model.predict calls."""
+    import cv2
+    h = w = 32
+    rng = np.random.default_rng(7)
+    src = tmp_path / "in"; src.mkdir()
+    for i in range(3):
+        cv2.imwrite(str(src / f"img{i}.png"), rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8))
+    models = [U.B200UNet(h, w, 3, 1, 0.5, "sigmoid", U.init_weights(3, 1, 0.5, seed=40 + j)) for j in range(2)]
+    x = rng.integers(0, 256, size=(2, h, w, 3), dtype=np.uint8)
+    before = [m.predict(x) for m in models]
+    F.create_pseudo_labels_im_ISIC_2018(models, h, w, 3, str(src), str(tmp_path / "out"), rgb=True, erode_kernel=0, dilate_kernel=0)
+    F.create_pseudo_labels_im_ISIC_2018(models, h, w, 3, str(src), str(tmp_path / "out2"), rgb=True, erode_kernel=3, dilate_kernel=3)
+    after = [m.predict(x) for m in models]
+    for a, b in zip(before, after):
+        same(a, b)

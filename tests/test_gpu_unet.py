@@ -284,7 +284,7 @@ def test_host_pipeline_multi_chunk_matches_single_calls(U, F):
     labels = np.empty((3, n, h, w), np.uint8); im = np.empty((n, h, w), np.uint8)
     out = np.empty_like(images); sz = np.empty(n, np.int64); pred = np.empty((3, n), np.int64)
     hs = (C.c_void_p * 2)(*[m.handle for m in models])
-    _lib.check(_lib.lib.imk_pseudo_label_binary_host(hs, 2, images.ctypes.data, n, 0.5, 0, 1, 1, out.ctypes.data,
+    _lib.check(_lib.lib.imk_pseudo_label_binary_host(hs, 2, images.ctypes.data, n, 0, 0.5, 0, 1, 1, out.ctypes.data,
                                                      labels.ctypes.data, im.ctypes.data, sz.ctypes.data, pred.ctypes.data, 5))
     same(labels, ref.labels); same(im, ref.im); same(out, ref.image); same(sz, ref.im_size); same(pred, ref.pred_size)
 

@@ -36,9 +36,9 @@ s = torch.cuda.current_stream().cuda_stream
 
 def step():
     if mc:
-        check(lib.imk_ensemble_im_multiclass(handles, M, img.data_ptr(), N, 1, 1, out.data_ptr(), lab.data_ptr(), im.data_ptr(), sz.data_ptr(), None, s))
+        check(lib.imk_ensemble_im_multiclass(handles, M, img.data_ptr(), N, 0, 1, 1, out.data_ptr(), lab.data_ptr(), im.data_ptr(), sz.data_ptr(), None, s))
     else:
-        check(lib.imk_ensemble_im_binary(handles, M, img.data_ptr(), N, 0.5, strict, 1, 1, out.data_ptr(), lab.data_ptr(), im.data_ptr(), sz.data_ptr(), pred.data_ptr(), s))
+        check(lib.imk_ensemble_im_binary(handles, M, img.data_ptr(), N, 0, 0.5, strict, 1, 1, out.data_ptr(), lab.data_ptr(), im.data_ptr(), sz.data_ptr(), pred.data_ptr(), s))
 
 
 for _ in range(2):
