@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libimk.so")
+LIB_PATH = os.environ.get("IMK_LIB") or os.path.join(_HERE, "libimk.so")     # IMK_LIB: A/B runs against another build
 
 IMK_ACT_SIGMOID, IMK_ACT_SOFTMAX = 0, 1
 IMK_IN_U8, IMK_IN_F32 = 0, 1

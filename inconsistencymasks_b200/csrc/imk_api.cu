@@ -21,6 +21,18 @@ void set_error(const char *fmt, ...) {
 }
 int64_t &launch_counter() { return g_launches; }
 
+int num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    if (!cache[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 // ---- per-kernel profiler ------------------------------------------------------------
 struct ProfRec { const char *name; int tag; cudaEvent_t a, b; };
 static thread_local bool g_prof_on = false;

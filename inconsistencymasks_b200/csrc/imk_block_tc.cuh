@@ -6,7 +6,8 @@
 
 namespace imk {
 
-constexpr int kBtMaxBlocks = 24;        // M blocks (128 flat positions) per stage per tile
+constexpr int kBtMaxBlocks = 24;
+constexpr int kBtHeadMaxK = 16;      // widest output layer the head stage takes (one 16-column TMEM group per block)        // M blocks (128 flat positions) per stage per tile
 
 struct BtStage {
     int taps, ksteps, n, nb;            // 1|9, Cin_p/16, Cout_p (UMMA N), M blocks
@@ -47,6 +48,20 @@ struct BtArgs {
     // 256-entry table of finished fp16 rows, built in fp32 at kernel start; the loader warps copy rows straight into the
     // 3x3 stage's operand buffer: v = x/255 * fw[0][ch] + fb[ch], clamped to [flo, fhi] (BN scale folded as for the stages)
     float fw[4][32], fb[32], flo[32], fhi[32];
+    // Head stage (level-0 decoder of a network with K <= 16 outputs): S4 = the output layer `out` (unet.py:63) as a 1x1
+    // stage on the block's own c9 tile (fp16, never written to HBM), fp32 weights as fp16 hi + lo (two MMAs per K step).
+    // Accumulators of `head_pf` consecutive M blocks share one 16-column TMEM group: block b uses the operand-B variant
+    // whose K weight columns sit at [s*K, s*K + K), s = b % head_pf, and accumulates into group b / head_pf.
+    // E4 turns a pixel's K logits into (head_mode 0) fp32 probabilities [N,H,W,K], (1) a byte of threshold votes
+    // (bit k = head k fires) or (2) the argmax class id -- one byte per pixel per model instead of the c9 map.
+    int has_s4, head_K, head_pf, head_ldw, head_mode, head_act, head_strict;
+    float head_thr, head_dstar;
+    BtStage s4;
+    int a3_off, Pn3;
+    float hb[16];
+    float *head_probs;
+    uint8_t *head_dec;
+    int dbg_skip;                       // first tile (of CTA 0) the timeline records (IMK_BT_TL_SKIP)
     long long *dbg;                     // optional timeline buffer (IMK_BT_TIMELINE=1): [3 roles][16 tiles][8 events] clocks of CTA 0
 };
 
@@ -59,6 +74,15 @@ struct FusedBlock {                     // one fused U-Net block of one model (d
     size_t smem = 0;
 };
 
+// What the head stage of a level-0 decoder block writes (fused_block_build kind 4)
+struct HeadOut {
+    int mode;                           // 0: fp32 probabilities, 1: threshold votes (bit k of a byte), 2: argmax class id
+    float thr, dstar;                   // mode 1: threshold; dstar > 0: the exact `1 + exp(-z) <= dstar` form of it
+    int strict;
+    float *probs;                       // mode 0: [n,H,W,K]
+    uint8_t *dec;                       // mode 1 / 2: [n,H,W]
+};
+
 struct ConvHost {                       // host view of one Conv2D (+BN) while imk_unet_create runs
     const float *hwio, *bias;
     const float *bn_scale, *bn_shift;   // folded BN (gamma / sqrt(var + eps), beta - mean * scale) or null
@@ -69,12 +93,13 @@ struct ConvHost {                       // host view of one Conv2D (+BN) while i
 int make_map(CUtensorMap *map, const void *base, int64_t n, int h, int w, int c, int box_w, int box_h);
 
 // kind: 0 FRONT (in 1x1, conv3, conv1 of level 0), 1 ENC (conv3, conv1), 2 DEC (conv1a, conv3, conv1b),
-//       3 FRONT for uint8 images with the input block computed by the loader (a chain of two).
+//       3 FRONT for uint8 images with the input block computed by the loader (a chain of two),
+//       4 DEC + head (conv1a, conv3, conv1b, out): L[3] is the output layer, `head_act` its activation.
 // Leaves fb.ok == false (and returns IMK_OK) when the block does not fit the resident-weight design.
-int fused_block_build(FusedBlock &fb, int kind, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned);
+int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned, int head_act = 0);
 // out_pool (optional, needs fused_block_can_pool): the 2x2 max-pooled map is written next to `out` by the same kernel.
 bool fused_block_can_pool(const FusedBlock &fb);
 int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo, __half *out, __half *out_pool, int64_t n,
-                       int swap_rb, int in_f32, cudaStream_t stream);
+                       int swap_rb, int in_f32, cudaStream_t stream, const HeadOut *head = nullptr);
 
 }  // namespace imk

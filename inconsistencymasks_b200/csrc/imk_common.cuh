@@ -11,7 +11,8 @@
 
 namespace imk {
 
-constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs (planning constant of the cost models)
+int num_sms();                 // SM count of the current device (persistent grids are sized from this)
 
 // ---- thread-local error / launch accounting --------------------------------
 void set_error(const char *fmt, ...);

@@ -476,10 +476,14 @@ int conv_tc_launch(const ConvLayer &L, const __half *in, const __half *in_lo, __
         if (rc) return rc;
     }
     const size_t smem = (size_t)a.act_bytes + kWSlots * a.stage_bytes + 3 * a.cout_p * 4 + (2 * kWSlots + kMaxMBlocks + 1) * 8 + 16;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        IMK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = 227 * 1024;
+    {   // the opt-in is per device (a process may drive several GPUs): once per device
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        IMK_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            IMK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     if (env_flag("IMK_TC_VERBOSE"))
         fprintf(stderr, "[imk] conv_tc %dx%d k%d %d->%d: strip %d rows, %d M blocks, TMEM %d cols, %d stages of %d B, act %d B\n", h, w, L.ks,

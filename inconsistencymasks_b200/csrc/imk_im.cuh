@@ -12,6 +12,26 @@ __device__ __forceinline__ uint32_t decide(float p, float thr, bool strict) {
     return strict ? (p > thr) : (p >= thr);
 }
 
+// sigmoid / softmax of one pixel's logits in place -- the ONE definition shared by every path
+template <int KMAX>
+__device__ __forceinline__ void pixel_activation(float (&p)[KMAX], int K, int act) {
+    if (act == IMK_ACT_SIGMOID) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) p[k] = __fdiv_rn(1.0f, __fadd_rn(1.0f, __expf(-p[k])));
+    } else {
+        float mx = p[0];
+#pragma unroll
+        for (int k = 1; k < KMAX; ++k) if (k < K) mx = fmaxf(mx, p[k]);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) { p[k] = __expf(__fsub_rn(p[k], mx)); sum = __fadd_rn(sum, p[k]); }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) p[k] = __fdiv_rn(p[k], sum);
+    }
+}
+
 // np.argmax (functions.py:3225): first index of the maximum, NaN is the maximum (the first NaN wins).
 // Floats are mapped to unsigned keys whose integer order is the float order with -0 == +0 and every NaN on top,
 // so that one strict integer compare per element implements the whole rule (about 8 instructions per element).

@@ -225,26 +225,6 @@ struct OutParams {                      // per model, in shared memory: w[K][c1p
     const float *b;                     // device [K]
 };
 
-// sigmoid / softmax of one pixel's logits in place -- the ONE definition shared by every path
-template <int KMAX>
-__device__ __forceinline__ void pixel_activation(float (&p)[KMAX], int K, int act) {
-    if (act == IMK_ACT_SIGMOID) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-            if (k < K) p[k] = __fdiv_rn(1.0f, __fadd_rn(1.0f, __expf(-p[k])));
-    } else {
-        float mx = p[0];
-#pragma unroll
-        for (int k = 1; k < KMAX; ++k) if (k < K) mx = fmaxf(mx, p[k]);
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-            if (k < K) { p[k] = __expf(__fsub_rn(p[k], mx)); sum = __fadd_rn(sum, p[k]); }
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) if (k < K) p[k] = __fdiv_rn(p[k], sum);
-    }
-}
-
 // run-time shapes: one thread = one pixel, sequential FMAs
 template <int KMAX>
 __device__ __forceinline__ void pixel_probs(const __half *__restrict__ x /*c1p halves of one pixel*/, int c1p,
@@ -588,6 +568,111 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
     }
 }
 
+// =============================================================================
+//  ensemble epilogue on head-stage decisions: every model's level-0 decoder kernel has already run its output layer
+//  and left ONE byte per pixel (bit k = head k fires, or the argmax class id).  This kernel only counts votes:
+//  reads M bytes + the image per pixel, writes label(s), IM, blanked image (uint8) and the per-image sizes.
+//  One thread = 16 consecutive pixels, every access 128-bit and warp-contiguous; SIMD-in-word byte arithmetic.
+//  MODE 0: K = 1 (functions.py:3104-3120)   1: K = 3 HeLa (functions.py:3185-3200)   2: multiclass (functions.py:3123-3137)
+// =============================================================================
+struct DecPtrs { const uint8_t *d[IMK_MAX_MODELS]; };
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+ensemble_votes_kernel(DecPtrs dec, int M, int64_t total_px, int64_t HW, int64_t N, int64_t plane_stride,
+                      const uint8_t *__restrict__ img, int c, int block_in, int block_out,
+                      uint8_t *__restrict__ img_out, uint8_t *__restrict__ labels, uint8_t *__restrict__ im_out,
+                      int64_t *__restrict__ im_size, int64_t *__restrict__ pred_size, unsigned long long *__restrict__ presence) {
+    constexpr int NK = MODE == 1 ? 3 : 1;
+    const int64_t n_groups = total_px / 16;                          // H, W are multiples of 16: a group never straddles images
+    const int64_t n_iter = (n_groups + 31) / 32 * 32;                // whole warps (the statistics are warp reductions)
+    const uint32_t m_rep = (uint32_t)M * 0x01010101u;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < n_iter; gi += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = gi < n_groups;
+        const int64_t px = gi * 16;
+        const int64_t n = live ? (int64_t)((uint32_t)px / (uint32_t)HW) : -1;       // chunks stay far below 2^31 pixels
+        uint32_t first[4] = {0, 0, 0, 0};
+        uint32_t cnt[NK][4], diff[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cnt[k][j] = 0;
+        for (int m = 0; m < M; ++m) {
+            const uint4 v = live ? ldg_stream(dec.d[m] + px) : make_uint4(0, 0, 0, 0);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            if (MODE == 2) {
+                if (m == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) first[j] = w[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) diff[j] |= w[j] ^ first[j];
+                }
+                if (presence) {                                      // class sets for lists_equal (functions.py:3226-3234)
+                    unsigned long long bits = 0ull;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) bits |= 1ull << ((w[j] >> (8 * e)) & 63u);
+                    warp_or_stat(presence, n < 0 ? -1 : n * M + m, live ? bits : 0ull, false);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NK; ++k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cnt[k][j] += (w[j] >> k) & 0x01010101u;
+            }
+        }
+        uint32_t lab[NK][4], im01[4] = {0, 0, 0, 0};
+        uint32_t im_cnt = 0, pred_cnt[NK];
+        if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                im01[j] = bytes_nonzero01(diff[j]);                  // class ids and their XORs are < 0x80
+                lab[0][j] = first[j] & ~bytes01_to_ff(im01[j]);      // agree ? class id : 0
+                im_cnt += __popc(im01[j]);
+            }
+            pred_cnt[0] = 0;
+        } else {
+            uint32_t all01[NK][4];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                pred_cnt[k] = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t nz = bytes_nonzero01(cnt[k][j]);                 // S != 0
+                    const uint32_t ne = bytes_nonzero01(cnt[k][j] ^ m_rep);         // S != M
+                    all01[k][j] = ne ^ 0x01010101u;
+                    const uint32_t mix = nz & ne;
+                    im01[j] |= mix;                                  // combined IM = max over heads
+                    im_cnt += __popc(mix);                           // HeLa: the SUM of the three head IM sizes
+                    pred_cnt[k] += __popc(all01[k][j]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NK; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)      // head 2 (HeLa position) stays raw: the host blanks the circle image drawn from it
+                    lab[k][j] = bytes01_to_ff((block_out && k < 2) ? (all01[k][j] & ~im01[j]) : all01[k][j]);
+        }
+        warp_add_stat(im_size, n, live ? im_cnt : 0u, false);
+        if (MODE != 2 && pred_size) {
+#pragma unroll
+            for (int k = 0; k < NK; ++k) warp_add_stat(pred_size + (int64_t)k * N, n, live ? pred_cnt[k] : 0u, false);
+        }
+        if (live) {
+            uint32_t imw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) imw[j] = bytes01_to_ff(im01[j]);
+#pragma unroll
+            for (int k = 0; k < NK; ++k)
+                stg_stream(labels + (int64_t)k * plane_stride + px, make_uint4(lab[k][0], lab[k][1], lab[k][2], lab[k][3]));
+            stg_stream(im_out + px, make_uint4(imw[0], imw[1], imw[2], imw[3]));
+            if (img_out) blank_image16_any(img, img_out, c, px, imw, block_in != 0);
+        }
+    }
+}
+
 __global__ void lists_equal_kernel2(const unsigned long long *__restrict__ presence, int M, int64_t N,
                                     uint8_t *__restrict__ lists_equal) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -659,7 +744,7 @@ namespace imk {
 
 int unet_reserve(imk_unet *net, int64_t n) {
     if (n <= net->cap_n) return IMK_OK;
-    if (net->ws) { cudaFree(net->ws); net->ws = nullptr; net->cap_n = 0; }
+    if (net->ws) { cudaFree(net->ws); net->ws = nullptr; net->cap_n = 0; net->dec = nullptr; }
     size_t total = 0;
     size_t off[5][3];
     for (int l = 0; l < 5; ++l) {
@@ -674,7 +759,10 @@ int unet_reserve(imk_unet *net, int64_t n) {
         }
         net->lvl[l].h = h; net->lvl[l].w = w; net->lvl[l].ch_p = chp;
     }
-    if (cudaMalloc(&net->ws, total) != cudaSuccess) { set_error("unet workspace: cudaMalloc(%zu) failed", total); return IMK_ENOMEM; }
+    const size_t dec_off = total;
+    total += ((size_t)n * net->desc.height * net->desc.width + 255) / 256 * 256;
+    if (cudaMalloc(&net->ws, total) != cudaSuccess) { cudaGetLastError(); set_error("unet workspace: cudaMalloc(%zu) failed", total); return IMK_ENOMEM; }
+    net->dec = reinterpret_cast<uint8_t *>((char *)net->ws + dec_off);
     net->ws_bytes = total;
     for (int l = 0; l < 5; ++l) {
         net->lvl[l].skip = reinterpret_cast<__half *>((char *)net->ws + off[l][0]);
@@ -705,9 +793,17 @@ static int launch_conv(imk_unet *net, int layer, const __half *in, const __half 
     return IMK_OK;
 }
 
-int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int64_t n, cudaStream_t stream) {
+int unet_mark_used(imk_unet *net, cudaStream_t stream) {
+    if (!net->last_use) IMK_CUDA(cudaEventCreateWithFlags(&net->last_use, cudaEventDisableTiming));
+    IMK_CUDA(cudaEventRecord(net->last_use, stream));
+    return IMK_OK;
+}
+
+int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int64_t n, cudaStream_t stream, const HeadOut *head) {
     int rc = unet_reserve(net, n);
     if (rc) return rc;
+    // a model has ONE workspace: whatever still reads it on another stream (the previous call's epilogue) goes first
+    if (net->last_use) IMK_CUDA(cudaStreamWaitEvent(stream, net->last_use, 0));
     const imk_unet_desc &d = net->desc;
     const ConvLayer *L = net->conv.data();
     Level *lv = net->lvl;
@@ -784,7 +880,11 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int
     x = lv[4].skip;
     // decoder: (up(x) + skip) conv1+BN -> a ; conv3 -> b ; conv1+BN -> a
     for (int l = 3; l >= 0; --l) {
-        if (fused && net->fb_dec[l].ok) {
+        if (l == 0 && head && unet_has_head(net)) {
+            IMK_PROFILE("block_head", li, stream);
+            if ((rc = fused_block_launch(net->fb_head, lv[l].skip, x, nullptr, nullptr, n, 0, 0, stream, head))) return rc;
+            li += 3;
+        } else if (fused && net->fb_dec[l].ok) {
             IMK_PROFILE("block_dec", li, stream);
             if ((rc = fused_block_launch(net->fb_dec[l], lv[l].skip, x, lv[l].a, nullptr, n, 0, 0, stream))) return rc;
             li += 3;
@@ -933,6 +1033,7 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
                 if ((rc = fused_block_build(net->fb_enc[l], 1, &host[1 + 2 * l], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
             for (int l = 0; l < 4; ++l)
                 if ((rc = fused_block_build(net->fb_dec[l], 2, &host[11 + 3 * (3 - l)], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
+            if (getenv("IMK_BT_HEAD") && !getenv("IMK_BT_NO_HEAD") && (rc = fused_block_build(net->fb_head, 4, &host[20], d.height, d.width, 0, net->owned, d.act_out))) return fail(rc);
         }
     }
     *out = net;
@@ -943,6 +1044,7 @@ extern "C" void imk_unet_destroy(imk_unet_t *net) {
     if (!net) return;
     for (void *p : net->owned) cudaFree(p);
     if (net->ws) cudaFree(net->ws);
+    if (net->last_use) cudaEventDestroy(net->last_use);
     if (net->stage_in) cudaFree(net->stage_in);
     if (net->stage_probs) cudaFree(net->stage_probs);
     delete net;
@@ -977,9 +1079,13 @@ extern "C" int imk_unet_forward(imk_unet_t *net, const void *images_dev, int in_
     const int64_t HW = (int64_t)d.height * d.width;
     for (int64_t n0 = 0; n0 < N; n0 += kMaxChunk) {
         const int64_t n = (N - n0 < kMaxChunk) ? N - n0 : kMaxChunk;
-        int rc = unet_trunk(net, (const char *)images_dev + n0 * HW * in_px_bytes, in_dtype, d.swap_rb, n, stream);
+        float *probs_c = probs_dev + n0 * HW * d.num_outputmasks;
+        const HeadOut ho{0, 0.f, 0.f, 0, probs_c, nullptr};
+        const bool head = unet_has_head(net);
+        int rc = unet_trunk(net, (const char *)images_dev + n0 * HW * in_px_bytes, in_dtype, d.swap_rb, n, stream, head ? &ho : nullptr);
         if (rc) return rc;
-        if ((rc = launch_out_probs(net, n, probs_dev + n0 * HW * d.num_outputmasks, stream))) return rc;
+        if (!head && (rc = launch_out_probs(net, n, probs_c, stream))) return rc;
+        if ((rc = unet_mark_used(net, stream))) return rc;
     }
     return IMK_OK;
 }
@@ -1063,6 +1169,16 @@ static int check_ensemble(imk_unet_t *const *nets, int M, const char *who) {
     return IMK_OK;
 }
 
+// largest d with RN(1 / d) >= thr (> thr when strict): the sigmoid decision becomes one compare (0 = not applicable)
+static float sigmoid_dstar(float thr, int strict) {
+    if (!(thr > 0.f && thr < 1.f)) return 0.f;
+    auto fires = [&](float dd) { const volatile float q = 1.0f / dd; return strict ? q > thr : q >= thr; };
+    float d0 = 1.0f / thr;
+    for (int it = 0; it < 64 && fires(nextafterf(d0, INFINITY)); ++it) d0 = nextafterf(d0, INFINITY);
+    for (int it = 0; it < 64 && !fires(d0); ++it) d0 = nextafterf(d0, 0.f);
+    return (fires(d0) && !fires(nextafterf(d0, INFINITY))) ? d0 : 0.f;
+}
+
 template <int KMAX, bool MC, int KFIX, int C1FIX>
 static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float thr, int strict, int64_t total_px, int64_t HW,
                       int64_t N, int64_t plane_stride, const uint8_t *img, int c, int block_in, int block_out, uint8_t *img_out, uint8_t *labels,
@@ -1071,15 +1187,7 @@ static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float 
     if constexpr (KFIX > 0) smem += (size_t)M * HeadMma<KFIX, C1FIX>::BFRAG_WORDS * 4 + 8 * (size_t)HeadMma<KFIX, C1FIX>::WARP_BYTES;
     IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC, KFIX, C1FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_1d(total_px, 256, 4);
-    // largest d with RN(1 / d) >= thr (> thr when strict): the sigmoid decision becomes one compare (0 = not applicable)
-    float dstar = 0.f;
-    if (!MC && KFIX > 0 && act == IMK_ACT_SIGMOID && thr > 0.f && thr < 1.f) {
-        auto fires = [&](float dd) { const volatile float q = 1.0f / dd; return strict ? q > thr : q >= thr; };
-        float d0 = 1.0f / thr;
-        for (int it = 0; it < 64 && fires(nextafterf(d0, INFINITY)); ++it) d0 = nextafterf(d0, INFINITY);
-        for (int it = 0; it < 64 && !fires(d0); ++it) d0 = nextafterf(d0, 0.f);
-        if (fires(d0) && !fires(nextafterf(d0, INFINITY))) dstar = d0;
-    }
+    const float dstar = (!MC && KFIX > 0 && act == IMK_ACT_SIGMOID) ? sigmoid_dstar(thr, strict) : 0.f;
     IMK_PROFILE("ensemble_im", -1, stream);
     ensemble_im_kernel<KMAX, MC, KFIX, C1FIX><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, dstar, total_px, HW, N, plane_stride, img, c,
                                                                block_in, block_out, img_out, labels, im, im_size, pred_size, presence);
@@ -1101,7 +1209,10 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
     if (!multiclass) IMK_REQUIRE(K == 1 || K == 3, "%s: binary IM needs K = 1 (ISIC) or 3 (HeLa), model has %d", who, K);
     IMK_REQUIRE(!lists_equal || K <= 64, "%s: lists_equal needs K <= 64", who);
     const int c1p = nets[0]->conv.back().cin_p;
-    for (int m = 0; m < M; ++m)
+    // head path: every model's level-0 decoder kernel also runs the output layer and leaves one decision byte per pixel
+    bool use_head = true;
+    for (int m = 0; m < M; ++m) use_head = use_head && unet_has_head(nets[m]);
+    for (int m = 0; m < M && !use_head; ++m)
         IMK_REQUIRE(nets[m]->conv.back().cin_p == c1p, "%s: models with different int(16*alpha) padding cannot share the fused epilogue", who);
     if (N == 0) return IMK_OK;
     const int64_t HW = (int64_t)d.height * d.width;
@@ -1113,7 +1224,7 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
         if (need > g_presence2_cap) {
             if (g_presence2) cudaFree(g_presence2);
             g_presence2 = nullptr; g_presence2_cap = 0;
-            if (cudaMalloc(&g_presence2, need) != cudaSuccess) { set_error("%s: cudaMalloc(%zu) failed", who, need); return IMK_ENOMEM; }
+            if (cudaMalloc(&g_presence2, need) != cudaSuccess) { cudaGetLastError(); set_error("%s: cudaMalloc(%zu) failed", who, need); return IMK_ENOMEM; }
             g_presence2_cap = need;
         }
         presence = g_presence2;
@@ -1125,9 +1236,11 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
     if (profiling_active()) n_streams = 1;                       // per-kernel times are only meaningful without overlap
     AuxStreams *aux = nullptr;
     if (n_streams > 1 && (rc = aux_streams(n_streams - 1, &aux))) return rc;
+    const float dstar = (!multiclass && d.act_out == IMK_ACT_SIGMOID) ? sigmoid_dstar(thr, strict) : 0.f;
     for (int64_t n0 = 0; n0 < N; n0 += kMaxChunk) {
         const int64_t n = (N - n0 < kMaxChunk) ? N - n0 : kMaxChunk;
         EnsPtrs ens{};
+        DecPtrs decs{};
         // fork: everything already in the caller's stream (uploads, the previous chunk's epilogue that still reads
         // the workspaces) precedes the auxiliary streams' work
         if (aux) {
@@ -1137,10 +1250,13 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
         for (int m = 0; m < M; ++m) {
             const int lane = m % n_streams;
             cudaStream_t sm = lane == 0 ? stream : aux->s[lane - 1];
-            if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, swap_rb ? 1 : 0, n, sm))) return rc;
+            if ((rc = unet_reserve(nets[m], n))) return rc;       // nets[m]->dec must exist before the HeadOut is formed
+            const HeadOut ho{multiclass ? 2 : 1, thr, dstar, strict, nullptr, nets[m]->dec};
+            if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, swap_rb ? 1 : 0, n, sm, use_head ? &ho : nullptr))) return rc;
             ens.c9[m] = nets[m]->lvl[0].a;
             ens.w[m] = nets[m]->conv.back().w_f32;
             ens.b[m] = nets[m]->conv.back().bias;
+            decs.d[m] = nets[m]->dec;
         }
         if (aux)                                                 // join before the epilogue
             for (int a = 0; a < n_streams - 1; ++a) {
@@ -1153,20 +1269,40 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
         uint8_t *im_c = im + n0 * HW;
         int64_t *im_size_c = im_size + n0;
         const int64_t total_px = n * HW;
-        rc = dispatch_head(K, c1p, [&](auto kmax, auto kfix, auto c1fix) -> int {
-            constexpr int KM = decltype(kmax)::value, KF = decltype(kfix)::value, CF = decltype(c1fix)::value;
+        if (use_head) {
+            IMK_REQUIRE(total_px < 0x7fffffffLL, "%s: chunk of %lld pixels", who, (long long)total_px);
+            const int grid = grid_1d(total_px / 16, 256, 8);
+            unsigned long long *pres_c = presence ? presence + n0 * M : nullptr;
+            int64_t *pred_c = (pred_size && !multiclass) ? pred_size + n0 : nullptr;
+            IMK_PROFILE("ensemble_votes", -1, stream);
             if (multiclass)
-                return launch_ens<KM, true, KF, CF>(ens, M, c1p, K, d.act_out, 0.f, 1, total_px, HW, N, N * HW, img_c, d.in_channels,
-                                                    block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
-                                                    nullptr, presence ? presence + n0 * M : nullptr, stream);
-            if constexpr (KM <= 4)                                // binary IM: K = 1 (ISIC) or 3 (HeLa), checked above
-                return launch_ens<KM < 3 ? (KM == 1 ? 1 : 4) : KM, false, KF, CF>(ens, M, c1p, K, d.act_out, thr, strict, total_px, HW, N, N * HW, img_c,
-                                                     d.in_channels, block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
-                                                     pred_size ? pred_size + n0 : nullptr, nullptr, stream);
-            set_error("%s: binary IM with K = %d", who, K);
-            return IMK_EINVAL;
-        });
-        if (rc) return rc;
+                ensemble_votes_kernel<2><<<grid, 256, 0, stream>>>(decs, M, total_px, HW, N, N * HW, img_c, d.in_channels, block_in, block_out,
+                                                                   img_out_c, labels + n0 * HW, im_c, im_size_c, nullptr, pres_c);
+            else if (K == 1)
+                ensemble_votes_kernel<0><<<grid, 256, 0, stream>>>(decs, M, total_px, HW, N, N * HW, img_c, d.in_channels, block_in, block_out,
+                                                                   img_out_c, labels + n0 * HW, im_c, im_size_c, pred_c, nullptr);
+            else
+                ensemble_votes_kernel<1><<<grid, 256, 0, stream>>>(decs, M, total_px, HW, N, N * HW, img_c, d.in_channels, block_in, block_out,
+                                                                   img_out_c, labels + n0 * HW, im_c, im_size_c, pred_c, nullptr);
+            IMK_LAUNCHED();
+        } else {
+            rc = dispatch_head(K, c1p, [&](auto kmax, auto kfix, auto c1fix) -> int {
+                constexpr int KM = decltype(kmax)::value, KF = decltype(kfix)::value, CF = decltype(c1fix)::value;
+                if (multiclass)
+                    return launch_ens<KM, true, KF, CF>(ens, M, c1p, K, d.act_out, 0.f, 1, total_px, HW, N, N * HW, img_c, d.in_channels,
+                                                        block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
+                                                        nullptr, presence ? presence + n0 * M : nullptr, stream);
+                if constexpr (KM <= 4)                                // binary IM: K = 1 (ISIC) or 3 (HeLa), checked above
+                    return launch_ens<KM < 3 ? (KM == 1 ? 1 : 4) : KM, false, KF, CF>(ens, M, c1p, K, d.act_out, thr, strict, total_px, HW, N, N * HW, img_c,
+                                                         d.in_channels, block_in, block_out, img_out_c, labels + n0 * HW, im_c, im_size_c,
+                                                         pred_size ? pred_size + n0 : nullptr, nullptr, stream);
+                set_error("%s: binary IM with K = %d", who, K);
+                return IMK_EINVAL;
+            });
+            if (rc) return rc;
+        }
+        for (int m = 0; m < M; ++m)
+            if ((rc = unet_mark_used(nets[m], stream))) return rc;
     }
     if (multiclass && lists_equal) {
         lists_equal_kernel2<<<(int)((N + 255) / 256), 256, 0, stream>>>(presence, M, N, lists_equal);

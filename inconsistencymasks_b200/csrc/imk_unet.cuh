@@ -37,10 +37,13 @@ struct imk_unet {
     imk::FusedBlock fb_enc[5];                  // [0] = FRONT (in + enc1), [1..3] = enc2..4, [4] = bottleneck (conv3 + conv1, no pool)
     imk::FusedBlock fb_dec[4];                  // decoder block that OUTPUTS level l
     imk::FusedBlock fb_front_u8;                // FRONT for uint8 images: input block on the loader warps, chain of two (kind 3)
+    imk::FusedBlock fb_head;                    // level-0 decoder + output layer + activation / decision (kind 4, K <= 16)
     std::vector<void *> owned;                  // device allocations freed at destroy
     // workspace (grown on demand), for `cap_n` images
     int64_t cap_n = 0;
     imk::Level lvl[5];
+    uint8_t *dec = nullptr;                     // per-pixel decision byte of the head stage (votes / class id), cap_n images
+    cudaEvent_t last_use = nullptr;             // recorded after the last consumer of the workspace; waited by the next trunk
     void *ws = nullptr;
     size_t ws_bytes = 0;
     void *stage_in = nullptr;                   // staging for *_host calls
@@ -53,7 +56,12 @@ namespace imk {
 
 // Runs the 23 hidden layers for images [n0, n0+n) and leaves c9 (decoder level-0
 // output, fp16 [n,H,W,C1p]) in net->lvl[0].a.  `images` points at image n0.
-int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int64_t n, cudaStream_t stream);
+// With `head` (and unet_has_head(net)) the last kernel also runs the output layer and writes what `head` asks for
+// instead of c9.
+int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int64_t n, cudaStream_t stream, const HeadOut *head = nullptr);
+inline bool unet_has_head(const imk_unet *net) { return net->engine == 2 && net->fb_head.ok; }
+// Call after the last kernel that reads the model's workspace has been enqueued on `stream`.
+int unet_mark_used(imk_unet *net, cudaStream_t stream);
 int unet_reserve(imk_unet *net, int64_t n);
 int64_t max_chunk();                    // images per trunk pass (bounds the workspace; IMK_CHUNK overrides the default)
 #define kMaxChunk (imk::max_chunk())

@@ -48,9 +48,6 @@ __all__ = [
     "get_pos_contours", "get_min_dist", "THRESHOLD",
 ]
 
-_FILES_PER_BATCH = 256
-
-
 def _torch():
     import torch
     if not torch.cuda.is_available():
@@ -145,12 +142,13 @@ def _predict_stack(models, images):
 
 
 def _run_batch(models, model_input, kind, *, threshold=THRESHOLD, blank_image=None, block_input=False,
-               block_output=False, erode_kernel=0, dilate_kernel=0, want_lists_equal=False, swap_rb=False):
+               block_output=False, erode_kernel=0, dilate_kernel=0, want_lists_equal=False, swap_rb=False, slot=None):
     """One batch through the device path.
 
     model_input: uint8 [N,H,W,c] in the channel order the models consume (unless swap_rb).
     blank_image: uint8 [N,H,W,c] to blank (the BGR array of the drivers) or None.
     kind: 'binary' (K=1, strict >), 'hela' (K=3, >=), 'multiclass'.
+    slot: optional ``_Slot`` whose pinned buffers receive the results of the fused host pipeline (the drivers).
     """
     torch = _torch()
     n, h, w, c = model_input.shape
@@ -170,20 +168,25 @@ def _run_batch(models, model_input, kind, *, threshold=THRESHOLD, blank_image=No
     if fused and not morph:
         # host pipeline: uploads / downloads overlapped with compute inside libimk
         src = np.ascontiguousarray(model_input)
-        labels = np.empty((planes, n, h, w), np.uint8)
-        im = np.empty((n, h, w), np.uint8)
-        im_size = np.empty(n, np.int64)
-        img_out = np.empty_like(src) if want_img else None
+        if slot is not None:
+            labels = slot.labels[:planes * n * h * w].reshape(planes, n, h, w)
+            im, im_size = slot.im[:n], slot.im_size[:n]
+            img_out = slot.img_out[:n] if want_img else None
+        else:
+            labels = np.empty((planes, n, h, w), np.uint8)
+            im = np.empty((n, h, w), np.uint8)
+            im_size = np.empty(n, np.int64)
+            img_out = np.empty_like(src) if want_img else None
         hs = _handles(models)
         if kind == "multiclass":
-            leq = np.empty(n, np.uint8) if want_lists_equal else None
+            leq = (slot.leq[:n] if slot is not None else np.empty(n, np.uint8)) if want_lists_equal else None
             check(lib.imk_pseudo_label_multiclass_host(hs, len(models), src.ctypes.data, n, int(swap_rb), k_bi, k_bo,
                                                        img_out.ctypes.data if want_img else None,
                                                        labels.ctypes.data, im.ctypes.data, im_size.ctypes.data,
                                                        leq.ctypes.data if leq is not None else None, 0))
             res.pred_size, res.lists_equal = None, leq
         else:
-            pred = np.empty((planes, n), np.int64)
+            pred = slot.pred[:planes * n].reshape(planes, n) if slot is not None else np.empty((planes, n), np.int64)
             check(lib.imk_pseudo_label_binary_host(hs, len(models), src.ctypes.data, n, int(swap_rb), float(threshold), strict, k_bi, k_bo,
                                                    img_out.ctypes.data if want_img else None,
                                                    labels.ctypes.data, im.ctypes.data, im_size.ctypes.data,
@@ -322,80 +325,185 @@ def _draw_positions(pos_raw, h, w, max_pos_circle_size, min_pos_circle_size):
 
 
 # --------------------------------------------------------------------------- a7 / a8 / a9 / a10
-def _batches(names):
-    for i in range(0, len(names), _FILES_PER_BATCH):
-        yield names[i:i + _FILES_PER_BATCH]
+# The per-directory drivers.  The reference decodes, predicts and encodes one file at a time (functions.py:2844-2887);
+# here a directory runs as a 3-slot software pipeline: a thread pool decodes the PNGs of batch i+1 into pinned host
+# buffers and encodes / writes the results of batch i-1 (cv2 releases the GIL) while libimk's host pipeline streams
+# batch i through the GPU.  File contents, file names and the returned statistic are those of the reference.
+_FILES_PER_BATCH = 512
+_IO_THREADS = max(4, min(32, os.cpu_count() or 4))
 
 
-def _mean_im_size(im_sizes):
-    return round(sum(im_sizes.values()) / len(im_sizes), 0)          # functions.py:2889 (banker's rounding)
+def _pinned(shape, dtype):
+    """Page-locked host array (asynchronous copies): a NumPy view of a pinned torch tensor."""
+    torch = _torch()
+    tdt = {np.uint8: torch.uint8, np.int64: torch.int64}[dtype]
+    return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+
+
+class _Slot:
+    """Host buffers of one batch in flight (flat, so that a short last batch still gets dense [planes][n] planes)."""
+
+    def __init__(self, cap, h, w, c, planes):
+        self.cap, self.h, self.w, self.c, self.planes = cap, h, w, c, planes
+        self.img = _pinned((cap, h, w, c), np.uint8)
+        self.img_out = _pinned((cap, h, w, c), np.uint8)
+        self.labels = _pinned((planes * cap * h * w,), np.uint8)
+        self.im = _pinned((cap, h, w), np.uint8)
+        self.im_size = _pinned((cap,), np.int64)
+        self.pred = _pinned((planes * cap,), np.int64)
+        self.leq = _pinned((cap,), np.uint8)
+
+
+def _shard_names(names, shard):
+    """(names of this rank, rank, world).  shard: None = automatic (an initialised torch.distributed group with more
+    than one rank shards the directory), False = never, (rank, world) = explicit."""
+    if shard is False:
+        return names, 0, 1
+    if shard is None or shard is True:
+        rank, world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+    else:
+        rank, world = int(shard[0]), int(shard[1])
+    if world <= 1:
+        return names, 0, 1
+    from .pool import shard_indices
+    ordered = sorted(names)                      # os.listdir order is arbitrary: every rank must see the same list
+    return [ordered[i] for i in shard_indices(len(ordered), rank, world)], rank, world
+
+
+def _mean_im_size(im_sizes, world=1):
+    """functions.py:2889: ``round(sum(im_sizes.values()) / len(im_sizes), 0)`` (banker's rounding); with a sharded
+    directory the integer sums are all-reduced first (one int64[3] exchange, no collective on the data path)."""
+    total, count = sum(int(v) for v in im_sizes.values()), len(im_sizes)
+    if world > 1:
+        from .pool import allreduce_stats
+        total, _, count = allreduce_stats(total, 0, count)
+    return round(total / count, 0)
+
+
+def _run_directory(models, kind, h, w, c, images_path, read_flags, run_kwargs, want_image, decide, store, shard=None):
+    """Pipelined per-directory loop shared by the three drivers.
+
+    decide(result, i) -> per-file context (or None to skip the gated outputs); store(slot_view, ctx, i, name) writes the
+    files of image i on a pool thread.  Returns ``(im_sizes dict, world)``."""
+    from concurrent.futures import ThreadPoolExecutor
+    names, _, world = _shard_names(os.listdir(images_path), shard)
+    im_sizes = {}
+    if not names:
+        return im_sizes, world
+    planes = 3 if kind == "hela" else 1
+    batches = [names[i:i + _FILES_PER_BATCH] for i in range(0, len(names), _FILES_PER_BATCH)]
+    cap = max(len(b) for b in batches)
+    slots = [_Slot(cap, h, w, c, planes) for _ in range(min(3, len(batches)))]
+    busy = [[] for _ in slots]
+
+    def load_one(slot, i, name):
+        image = cv2.imread(os.path.join(images_path, name), *read_flags)
+        if image is None:                            # the reference fails on `image.reshape` / cvtColor of None
+            raise AttributeError(f"cv2.imread returned None for {os.path.join(images_path, name)!r}")
+        slot.img[i] = image.reshape(h, w, c)
+
+    with ThreadPoolExecutor(_IO_THREADS) as io:
+        def start_load(bi):
+            k = bi % len(slots)
+            for f in busy[k]:
+                f.result()                           # the slot's previous results are on disk (re-raises I/O errors)
+            busy[k] = []
+            return [io.submit(load_one, slots[k], i, nm) for i, nm in enumerate(batches[bi])]
+
+        loads = start_load(0)
+        for bi, bnames in enumerate(batches):
+            for f in loads:
+                f.result()
+            if bi + 1 < len(batches):
+                loads = start_load(bi + 1)
+            slot, n = slots[bi % len(slots)], len(bnames)
+            batch = slot.img[:n]
+            r = _run_batch(models, batch, kind, blank_image=batch if want_image else None, slot=slot, **run_kwargs)
+            ctxs = []
+            for i, nm in enumerate(bnames):
+                im_sizes[nm[:-4]] = int(r.im_size[i])
+                ctxs.append(decide(r, i))
+            busy[bi % len(slots)] = [io.submit(store, r, ctxs[i], i, nm) for i, nm in enumerate(bnames)]
+        for b in busy:
+            for f in b:
+                f.result()
+    return im_sizes, world
 
 
 def create_pseudo_labels_im_ISIC_2018(models, h, w, c, images_path, main_output_path, rgb=True, erode_kernel=5,
-                                      dilate_kernel=5, block_input=True, block_output=True, filter_bad_predictions=True):
-    """functions.py:2832-2891.  Returns ``mean_im_size`` (float)."""
+                                      dilate_kernel=5, block_input=True, block_output=True, filter_bad_predictions=True,
+                                      shard=None):
+    """functions.py:2832-2891.  Returns ``mean_im_size`` (float).  ``shard``: see ``_shard_names``."""
     out_img, out_mask, out_im = (os.path.join(main_output_path, d) for d in ("images", "masks", "im"))
     for d in (out_img, out_mask, out_im):
         os.makedirs(d, exist_ok=True)
-    im_sizes = {}
-    for names in _batches(os.listdir(images_path)):
-        disk = np.stack([cv2.imread(os.path.join(images_path, nm)).reshape(h, w, c) for nm in names])
-        swap = bool(rgb) and c == 3                      # cv2.cvtColor(image, COLOR_BGR2RGB), functions.py:2847-2848
-        r = _run_batch(models, disk, "binary", threshold=THRESHOLD, blank_image=disk, block_input=block_input,
-                       block_output=block_output, erode_kernel=erode_kernel, dilate_kernel=dilate_kernel, swap_rb=swap)
-        for i, nm in enumerate(names):
-            im_size, pred_size = int(r.im_size[i]), int(r.pred_size[0, i])
-            im_sizes[nm[:-4]] = im_size
-            write = (pred_size > im_size and pred_size > 0) if filter_bad_predictions else True
-            if write:
-                cv2.imwrite(os.path.join(out_img, nm), r.image[i] if c == 3 else r.image[i, ..., 0])
-                cv2.imwrite(os.path.join(out_mask, nm), r.labels[0, i])
-            cv2.imwrite(os.path.join(out_im, nm), r.im[i])
-    return _mean_im_size(im_sizes)
+    swap = bool(rgb) and c == 3                          # cv2.cvtColor(image, COLOR_BGR2RGB), functions.py:2847-2848
+
+    def decide(r, i):
+        im_size, pred_size = int(r.im_size[i]), int(r.pred_size[0, i])
+        return (pred_size > im_size and pred_size > 0) if filter_bad_predictions else True
+
+    def store(r, write, i, nm):
+        if write:
+            cv2.imwrite(os.path.join(out_img, nm), r.image[i] if c == 3 else r.image[i, ..., 0])
+            cv2.imwrite(os.path.join(out_mask, nm), r.labels[0, i])
+        cv2.imwrite(os.path.join(out_im, nm), r.im[i])
+
+    kw = dict(threshold=THRESHOLD, block_input=block_input, block_output=block_output, erode_kernel=erode_kernel,
+              dilate_kernel=dilate_kernel, swap_rb=swap)
+    im_sizes, world = _run_directory(models, "binary", h, w, c, images_path, (), kw, True, decide, store, shard)
+    return _mean_im_size(im_sizes, world)
 
 
 def create_pseudo_labels_im_hela(models, h, w, c, images_path, main_output_path, erode_kernel=5, dilate_kernel=5,
-                                 block_input=True, block_output=True, max_pos_circle_size=8, min_pos_circle_size=3):
+                                 block_input=True, block_output=True, max_pos_circle_size=8, min_pos_circle_size=3,
+                                 shard=None):
     """functions.py:2895-2984.  Returns ``mean_im_size`` (float)."""
     outs = {d: os.path.join(main_output_path, d) for d in ("brightfield", "alive", "dead", "mod_position", "im")}
     for d in outs.values():
         os.makedirs(d, exist_ok=True)
-    im_sizes = {}
-    for names in _batches(os.listdir(images_path)):
-        gray = np.stack([cv2.imread(os.path.join(images_path, nm), 0).reshape(h, w, c) for nm in names])
-        r = _run_batch(models, gray, "hela", threshold=THRESHOLD, blank_image=gray, block_input=block_input,
-                       block_output=block_output, erode_kernel=erode_kernel, dilate_kernel=dilate_kernel, swap_rb=False)
-        for i, nm in enumerate(names):
-            im_sizes[nm[:-4]] = int(r.im_size[i])
-            pos = _draw_positions(r.labels[2, i], h, w, max_pos_circle_size, min_pos_circle_size)
-            if block_output:
-                pos[r.im[i] > 0] = 0                     # functions.py:2974, on the host-drawn circles
-            cv2.imwrite(os.path.join(outs["brightfield"], nm), r.image[i, ..., 0])
-            cv2.imwrite(os.path.join(outs["alive"], nm), r.labels[0, i])
-            cv2.imwrite(os.path.join(outs["dead"], nm), r.labels[1, i])
-            cv2.imwrite(os.path.join(outs["mod_position"], nm), pos)
-            cv2.imwrite(os.path.join(outs["im"], nm), r.im[i])
-    return _mean_im_size(im_sizes)
+
+    def store(r, _ctx, i, nm):
+        pos = _draw_positions(r.labels[2, i], h, w, max_pos_circle_size, min_pos_circle_size)   # host geometry, on the pool
+        if block_output:
+            pos[r.im[i] > 0] = 0                         # functions.py:2974, on the host-drawn circles
+        cv2.imwrite(os.path.join(outs["brightfield"], nm), r.image[i, ..., 0])
+        cv2.imwrite(os.path.join(outs["alive"], nm), r.labels[0, i])
+        cv2.imwrite(os.path.join(outs["dead"], nm), r.labels[1, i])
+        cv2.imwrite(os.path.join(outs["mod_position"], nm), pos)
+        cv2.imwrite(os.path.join(outs["im"], nm), r.im[i])
+
+    kw = dict(threshold=THRESHOLD, block_input=block_input, block_output=block_output, erode_kernel=erode_kernel,
+              dilate_kernel=dilate_kernel, swap_rb=False)
+    im_sizes, world = _run_directory(models, "hela", h, w, c, images_path, (0,), kw, True, lambda r, i: None, store, shard)
+    return _mean_im_size(im_sizes, world)
 
 
 def create_pseudo_labels_im_multiclass(models, h, w, c, images_path, main_output_path, rgb=True, erode_kernel=5,
-                                       dilate_kernel=5, block_input=True, block_output=True, filter_unequal_class_pred=False):
+                                       dilate_kernel=5, block_input=True, block_output=True, filter_unequal_class_pred=False,
+                                       shard=None):
     """functions.py:2988-3070.  Returns ``mean_im_size`` (float)."""
     out_img, out_mask, out_im = (os.path.join(main_output_path, d) for d in ("images", "masks", "im"))
     for d in (out_img, out_mask, out_im):
         os.makedirs(d, exist_ok=True)
-    im_sizes = {}
-    for names in _batches(os.listdir(images_path)):
-        disk = np.stack([cv2.imread(os.path.join(images_path, nm)).reshape(h, w, c) for nm in names])
-        swap = bool(rgb) and c == 3
-        r = _run_batch(models, disk, "multiclass", blank_image=disk, block_input=block_input, block_output=block_output,
-                       erode_kernel=erode_kernel, dilate_kernel=dilate_kernel,
-                       want_lists_equal=bool(filter_unequal_class_pred), swap_rb=swap)
-        for i, nm in enumerate(names):
-            im_sizes[nm[:-4]] = int(r.im_size[i])
-            write = bool(r.lists_equal[i]) if filter_unequal_class_pred else True
-            if write:
-                cv2.imwrite(os.path.join(out_img, nm), r.image[i] if c == 3 else r.image[i, ..., 0])
-                cv2.imwrite(os.path.join(out_mask, nm), r.labels[0, i])
-            cv2.imwrite(os.path.join(out_im, nm), r.im[i])
-    return _mean_im_size(im_sizes)
+    swap = bool(rgb) and c == 3
+
+    def decide(r, i):
+        return bool(r.lists_equal[i]) if filter_unequal_class_pred else True
+
+    def store(r, write, i, nm):
+        if write:
+            cv2.imwrite(os.path.join(out_img, nm), r.image[i] if c == 3 else r.image[i, ..., 0])
+            cv2.imwrite(os.path.join(out_mask, nm), r.labels[0, i])
+        cv2.imwrite(os.path.join(out_im, nm), r.im[i])
+
+    kw = dict(block_input=block_input, block_output=block_output, erode_kernel=erode_kernel, dilate_kernel=dilate_kernel,
+              want_lists_equal=bool(filter_unequal_class_pred), swap_rb=swap)
+    im_sizes, world = _run_directory(models, "multiclass", h, w, c, images_path, (), kw, True, decide, store, shard)
+    return _mean_im_size(im_sizes, world)

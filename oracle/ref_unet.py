@@ -92,28 +92,71 @@ def _bn(x, cur):
     return x * scale.view(1, -1, 1, 1) + (b - mu * scale).view(1, -1, 1, 1)
 
 
+def _h(x):
+    """Round to fp16 and back: the value an fp16 activation / weight buffer holds."""
+    return x.to(torch.float16).to(torch.float32)
+
+
+def _layer(x, cur, bn, storage, first=False):
+    """Conv2D + ReLU (+ BatchNormalization) -- unet.py:6-7, 12-16, 24-28, 34-41.
+
+    storage == "fp32": the plain fp32 arithmetic.  storage == "fp16": the same layer with the ROUNDING POINTS of a
+    mixed-precision execution that keeps activations and hidden-layer weights in fp16 and accumulates in fp32 (the
+    reference runs ``mixed_float16``, 09_ISIC_2018_IM.py:16): inputs are fp16 values already, the weights are rounded to
+    fp16 (with the BN scale folded in, ``relu(v) * s + t == max(s * v + t, t)`` for ``s > 0``, ``min`` for ``s < 0``),
+    bias / shift are added in fp32 and the layer output is rounded to fp16 ONCE.  The first layer keeps fp32 weights.
+    """
+    if storage == "fp32":
+        y = _conv_act(x, cur)
+        return _bn(y, cur) if bn else y
+    k, b = cur.take(2)
+    pad = k.shape[0] // 2
+    if bn:
+        g, be, mu, var = cur.take(4)
+        scale = g / torch.sqrt(var + BN_EPS)
+        shift = be - mu * scale
+    else:
+        scale, shift = torch.ones_like(b), torch.zeros_like(b)
+    w = k * scale.view(1, 1, 1, -1)
+    if not first:
+        w = _h(w)
+    v = F.conv2d(x, w.permute(3, 2, 0, 1).contiguous(), None, padding=pad) + (scale * b + shift).view(1, -1, 1, 1)
+    t = shift.view(1, -1, 1, 1)
+    pos = (scale > 0).view(1, -1, 1, 1)
+    zero = (scale == 0).view(1, -1, 1, 1)
+    out = torch.where(pos, torch.maximum(v, t), torch.minimum(v, t))
+    out = torch.where(zero, t.expand_as(out), out)
+    return _h(out)
+
+
 @torch.no_grad()
-def forward(images, weights, actifuout="sigmoid", return_logits=False):
+def forward(images, weights, actifuout="sigmoid", return_logits=False, storage="fp32"):
     """``model.predict`` -- unet.py:46-67.
 
     images: uint8 or float ``[N, H, W, c]`` NHWC; weights: the 104 arrays.
     Returns float32 ``[N, H, W, K]`` probabilities (or pre-activation logits).
+    ``storage="fp16"`` models fp16 activation / weight storage with fp32 accumulation (see ``_layer``): the
+    mixed-precision twin of the fp32 oracle, used to separate "fp16 storage" from "kernel error" in the GPU tests.
     """
+    if storage not in ("fp32", "fp16"):
+        raise ValueError(storage)
     x = torch.from_numpy(np.ascontiguousarray(images)).to(torch.float32).permute(0, 3, 1, 2)
     cur = _Cursor(weights)
     x = x / 255.0                                   # unet.py:5
-    x = _bn(_conv_act(x, cur), cur)                 # unet.py:6-7
+    x = _layer(x, cur, True, storage, first=True)   # unet.py:6-7
     skips = []
     for _ in range(4):                              # unet.py:51-54
-        x = _bn(_conv_act(_conv_act(x, cur), cur), cur)
+        x = _layer(_layer(x, cur, False, storage), cur, True, storage)
         skips.append(x)
         x = F.max_pool2d(x, 2)
-    x = _bn(_conv_act(_conv_act(x, cur), cur), cur)  # unet.py:56
+    x = _layer(_layer(x, cur, False, storage), cur, True, storage)  # unet.py:56
     for skip in reversed(skips):                    # unet.py:58-61
         u = F.interpolate(x, scale_factor=2, mode="nearest") + skip
-        x = _bn(_conv_act(u, cur), cur)
-        x = _bn(_conv_act(_conv_act(x, cur), cur), cur)
-    logits = _conv_act(x, cur, relu=False)          # unet.py:63
+        if storage == "fp16":
+            u = _h(u)                               # an fp16 add
+        x = _layer(u, cur, True, storage)
+        x = _layer(_layer(x, cur, False, storage), cur, True, storage)
+    logits = _conv_act(x, cur, relu=False)          # unet.py:63 (fp32 output layer)
     assert cur.i == len(cur.w), "weight list length does not match the layer plan"
     if return_logits:
         out = logits

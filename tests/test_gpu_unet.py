@@ -48,6 +48,10 @@ CASES = [
     (32, 32, 3, 9, 1.25, "softmax"),    # widths 20, 40, 80, 160, 320: not multiples of 16
     (16, 16, 3, 1, 0.75, "sigmoid"),    # 1x1 bottleneck, widths 12..192
     (208, 416, 3, 35, 1.0, "softmax"),  # Cityscapes full size: 13x26 bottleneck (odd tile counts)
+    (32, 32, 1, 2, 1.0, "softmax"),     # head stage, generic class counts: K = 2 (8 blocks per TMEM group)
+    (32, 48, 3, 5, 0.5, "softmax"),     # K = 5 (2 blocks per group, 8-column loads)
+    (48, 32, 3, 12, 1.0, "sigmoid"),    # K = 12 (one block per group, 16-column loads)
+    (32, 32, 3, 16, 2.0, "softmax"),    # K = 16 on 32 channels (two K steps in the head stage)
 ]
 
 
@@ -207,7 +211,9 @@ def test_fused_multiclass_ties_and_near_ties(U, F, K):
 
 
 @pytest.mark.parametrize("kind,c,K,alpha,act", [("binary", 3, 1, 0.5, "sigmoid"), ("hela", 1, 3, 1.0, "sigmoid"),
-                                                ("multiclass", 3, 9, 1.0, "softmax"), ("multiclass", 3, 35, 1.0, "softmax")])
+                                                ("multiclass", 3, 9, 1.0, "softmax"), ("multiclass", 3, 35, 1.0, "softmax"),
+                                                ("multiclass", 3, 2, 1.0, "softmax"), ("multiclass", 3, 5, 2.0, "softmax"),
+                                                ("multiclass", 1, 12, 1.0, "sigmoid"), ("multiclass", 3, 16, 0.5, "softmax")])
 @pytest.mark.parametrize("M", [1, 2, 3])
 def test_fused_ensemble_equals_predict_then_im(U, F, kind, c, K, alpha, act, M):
     """The fused path (no fp32 map in HBM) must give, bit for bit, what the reference's own
