@@ -22,7 +22,7 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libimk.so")
 SOURCES = ["imk_api.cu", "imk_im.cu", "imk_morph.cu", "imk_unet.cu", "imk_conv_tc.cu", "imk_block_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("IMK_BUILD_FLAGS", "").split()
 
 
 def _nvcc() -> str:

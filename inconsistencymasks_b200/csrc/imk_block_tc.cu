@@ -54,16 +54,23 @@ constexpr uint32_t kBtSuspendNs = 20000;
 constexpr int kBtSmemMax = 227 * 1024;
 constexpr int kBtSmemMax2 = 112 * 1024;
 constexpr int bt_threads(int ew, int lw) { return (ew + 1 + lw + 1) * 32; }
-constexpr int kBtNumBars = 11 + 4 * kBtMaxBlocks;
+constexpr int kBtNumBars = 10 + 3 * kBtMaxBlocks;
 
 namespace {
 
-// timeline probe: role 0 = epilogue warp 0, 1 = MMA warp, 2 = loader warp 0 (CTA 0, first 16 tiles)
+// timeline probe: role 0 = epilogue warp 0, 1 = MMA warp, 2 = loader warp 0 (CTA 0, 16 tiles from a.dbg_skip).
+// Compiled in only with -DIMK_BT_TIMELINE_BUILD (IMK_BUILD_FLAGS=-DIMK_BT_TIMELINE_BUILD python -m inconsistencymasks_b200.build):
+// measured (r2l), the dormant probes alone cost the block kernels 3-9 % -- they sit on the MMA warp's issue path.
+#ifdef IMK_BT_TIMELINE_BUILD
 #define BT_TL(role, i, ev)                                                                         \
     do {                                                                                           \
         if (a.dbg && blockIdx.x == 0 && (i) >= a.dbg_skip && (i) < a.dbg_skip + 16 && (threadIdx.x & 31) == 0) \
             a.dbg[((role) * 16 + (int)((i) - a.dbg_skip)) * 8 + (ev)] = clock64();                 \
     } while (0)
+
+#else
+#define BT_TL(role, i, ev) do { } while (0)
+#endif
 
 // ---- PTX wrappers ----------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -71,6 +78,11 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// arrive without release semantics: the barrier only tells the MMA warp that TMEM has been read (ordered by
+// tcgen05.wait::ld + tcgen05.fence); a releasing arrive would first wait for the warp's global stores to be acknowledged
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -103,18 +115,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
-}
-template <int N>
-__device__ __forceinline__ void tc_ldn(uint32_t taddr, uint32_t (&r)[N]) {
-    static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16, "tcgen05.ld.32x32b shapes");
-    if constexpr (N == 1) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
-    if constexpr (N == 2) asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
-    if constexpr (N == 4)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-    if constexpr (N == 8)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-    if constexpr (N == 16) tc_ld16(taddr, r);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
@@ -254,145 +254,136 @@ __device__ __forceinline__ uint4 max_h8(const uint4 &v, const uint4 &u) {
     return r4;
 }
 
-// ---- head stage epilogue: one pixel's K logits (TMEM columns) -> probabilities / votes / class id -----------------
+// ---- head: one pixel's K logits -> probabilities / votes / class id ---------------------------------------------
 // The arithmetic after the logits is the ONE definition every path shares (pixel_activation, decide, argmax_step):
 // mode 0 is what .predict returns, modes 1 / 2 are exactly `decide(p)` / `np.argmax(p)` of those probabilities.
-template <int LDW, int KFIX>
-__device__ __forceinline__ void head_pixel(const BtArgs &a, const uint32_t (&r)[LDW], long long pix) {
-    const int K = KFIX > 0 ? KFIX : a.head_K;
-    constexpr int KM = KFIX > 0 ? KFIX : LDW;
-    float p[KM];
-#pragma unroll
-    for (int k = 0; k < KM; ++k) p[k] = __fadd_rn(__uint_as_float(r[k]), a.hb[k]);
+template <int K>
+__device__ __forceinline__ void head_pixel(const BtArgs &a, float (&p)[K], long long pix) {
     if (a.head_mode == 0) {
-        pixel_activation<KM>(p, K, a.head_act);
+        pixel_activation<K>(p, K, a.head_act);
         float *dst = a.head_probs + pix * K;
 #pragma unroll
-        for (int k = 0; k < KM; ++k) if (k < K) dst[k] = p[k];
+        for (int k = 0; k < K; ++k) dst[k] = p[k];
     } else if (a.head_mode == 1) {
         uint32_t bits = 0;
         if (a.head_act == IMK_ACT_SIGMOID && a.head_dstar > 0.f) {
             // threshold of the sigmoid without its division: RN(1 / d) is monotonic in d = 1 + exp(-z), so "p >= thr"
             // (or ">") is exactly "d <= dstar" with dstar found on the host by exact fp32 division
 #pragma unroll
-            for (int k = 0; k < KM; ++k)
-                if (k < K) bits |= (__fadd_rn(1.0f, __expf(-p[k])) <= a.head_dstar ? 1u : 0u) << k;
+            for (int k = 0; k < K; ++k) bits |= (__fadd_rn(1.0f, __expf(-p[k])) <= a.head_dstar ? 1u : 0u) << k;
         } else {
-            pixel_activation<KM>(p, K, a.head_act);
+            pixel_activation<K>(p, K, a.head_act);
 #pragma unroll
-            for (int k = 0; k < KM; ++k) if (k < K) bits |= decide(p[k], a.head_thr, a.head_strict != 0) << k;
+            for (int k = 0; k < K; ++k) bits |= decide(p[k], a.head_thr, a.head_strict != 0) << k;
         }
         a.head_dec[pix] = (uint8_t)bits;
     } else {
+        pixel_activation<K>(p, K, a.head_act);
         int arg = 0;
-        bool fast_arg = false;
-        if (a.head_act == IMK_ACT_SOFTMAX) {
-            // argmax of the softmax without its K divisions: p_k = e_k / sum is monotonic in e_k, and two numerators more
-            // than 2^-22 apart (relative) cannot round to the same quotient, so the first maximum of e is the first
-            // maximum of p unless another numerator is that close to it (or a NaN is around) -- only then the exact
-            // probabilities are formed, with pixel_activation's operations
-            float mx = p[0];
+        float best = p[0];
 #pragma unroll
-            for (int k = 1; k < KM; ++k) if (k < K) mx = fmaxf(mx, p[k]);
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < KM; ++k) if (k < K) { p[k] = __expf(__fsub_rn(p[k], mx)); sum = __fadd_rn(sum, p[k]); }
-            float best = p[0];
-#pragma unroll
-            for (int k = 1; k < KM; ++k) if (k < K && p[k] > best) { best = p[k]; arg = k; }
-            const float lim = best * 0.99999976f;
-            int close = 0;
-#pragma unroll
-            for (int k = 0; k < KM; ++k) if (k < K) close += (p[k] >= lim) ? 1 : 0;
-            fast_arg = close == 1 && sum == sum;
-            if (!fast_arg) {
-#pragma unroll
-                for (int k = 0; k < KM; ++k) if (k < K) p[k] = __fdiv_rn(p[k], sum);
-            }
-        } else {
-            pixel_activation<KM>(p, K, a.head_act);
-        }
-        if (!fast_arg) {
-            arg = 0;
-            float best = p[0];
-#pragma unroll
-            for (int k = 1; k < KM; ++k) if (k < K) argmax_step(p[k], k, best, arg);
-        }
+        for (int k = 1; k < K; ++k) argmax_step(p[k], k, best, arg);
         a.head_dec[pix] = (uint8_t)arg;
     }
 }
 
-// E4(j) of one epilogue warp: head accumulators of tile j -> every pixel's output, straight to HBM (1 byte or K floats
-// per pixel: nothing worth staging).  Warp w owns TMEM lanes 32 * (w % 4) of the M blocks w / 4 (mod G).
-template <int G>
-__device__ __forceinline__ void head_epilogue(const BtArgs &a, uint32_t tmem, uint64_t *acc4_full, uint64_t *e4_done, long long j) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, g = warp >> 2;
+// logits of one pixel from 16 finished channels (packed fp16, as they would have been stored): p[k] += sum_c x_c * w[k][c]
+// in channel order with fp32 FMAs -- weights are constant-bank operands of the FFMA itself
+template <int K, int CH>
+__device__ __forceinline__ void head_fma16(const BtArgs &a, const uint4 &lo, const uint4 &hi, float (&p)[K]) {
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float2 x = __half22float2(*reinterpret_cast<const __half2 *>(&w[q]));
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            p[k] = __fmaf_rn(x.x, a.hw[k][16 * CH + 2 * q], p[k]);
+            p[k] = __fmaf_rn(x.y, a.hw[k][16 * CH + 2 * q + 1], p[k]);
+        }
+    }
+}
+
+// E3 of the head variant for one epilogue warp: S3 accumulators -> c9 row (ReLU + BN, fp16) -> logits -> output.
+// NCH = 1: two BLOCKS per TMEM wait; NCH = 2: the two 16-channel chunks of one block per wait (as epi_stage does).
+template <int NCH, int K, int G>
+__device__ __forceinline__ void head_stage(const BtArgs &a, uint32_t tmem, int g, int q, int lane, uint64_t *acc_full, uint32_t parity,
+                                           int n, int y0, int x0) {
     const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
-    int n, y0, x0;
-    tile_coords(a, (long long)blockIdx.x + j * gridDim.x, n, y0, x0);
-    const uint32_t par_ = (uint32_t)(j & 1);
     const long long img0 = (long long)n * a.H * a.W;
-    // S4 is a handful of MMAs: wait for all of it once, then keep the TMEM loads of several blocks in flight before the
-    // one wait::ld (a visit per block would pay the load latency per block: the epilogue warps are latency-bound)
-    mbar_wait(&acc4_full[a.s4.nb - 1], par_);
-    __syncwarp();
-    tc_fence_after();
-    auto run = [&](auto ldw, auto kfix) {
-        constexpr int LDW = decltype(ldw)::value, KF = decltype(kfix)::value;
-        constexpr int NB = LDW >= 16 ? 1 : (LDW >= 8 ? 2 : 3);                    // blocks in flight (nb / G is 2..3 for the level-0 tiles)
-        for (int b0 = g; b0 < a.s4.nb; b0 += NB * G) {
-            uint32_t r[NB][LDW];
+    auto finish = [&](float (&p)[K], int b) {
+        const int m = b * 128 + q * 32 + lane;
+        const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
+        const int y = y0 + ro, x = x0 + co;
+        if (ro < a.Th && co < a.Tw && y < a.H && x < a.W) head_pixel<K>(a, p, img0 + (long long)y * a.W + x);
+    };
+    auto init = [&](float (&p)[K]) {
 #pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                const int b = b0 + t * G;
-                if (b < a.s4.nb) {                                               // warp-uniform
-                    const int grp = b / a.head_pf, slot = b - grp * a.head_pf;
-                    tc_ldn<LDW>(tmem + lane_base + (uint32_t)(a.s4.col + grp * 16 + slot * a.head_K), r[t]);
-                }
-            }
+        for (int k = 0; k < K; ++k) p[k] = a.hb[k];
+    };
+    const int nb = a.s3.nb;
+    if constexpr (NCH == 1) {
+        for (int b = g; b < nb; b += 2 * G) {
+            const bool two = b + G < nb;                             // warp-uniform
+            mbar_wait(&acc_full[two ? b + G : b], parity);           // blocks complete in order
+            __syncwarp();
+            tc_fence_after();
+            uint32_t r0[16], r1[16];
+            tc_ld16(tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), r0);
+            if (two) tc_ld16(tmem + lane_base + (uint32_t)(a.s3.col + (b + G) * a.s3.n), r1);
             tc_wait_ld();
-#pragma unroll
-            for (int t = 0; t < NB; ++t) {
-                const int b = b0 + t * G;
-                if (b < a.s4.nb) {
-                    const int m = b * 128 + q * 32 + lane;
-                    const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
-                    const int y = y0 + ro, x = x0 + co;
-                    if (ro < a.Th && co < a.Tw && y < a.H && x < a.W) head_pixel<LDW, KF>(a, r[t], img0 + (long long)y * a.W + x);
-                }
+            uint4 lo, hi;
+            float p[K];
+            epi16<2, 0>(a, r0, true, lo, hi);
+            init(p);
+            head_fma16<K, 0>(a, lo, hi, p);
+            finish(p, b);
+            if (two) {
+                epi16<2, 0>(a, r1, true, lo, hi);
+                init(p);
+                head_fma16<K, 0>(a, lo, hi, p);
+                finish(p, b + G);
             }
         }
-    };
-    using std::integral_constant;
-    switch (a.head_K) {
-        case 1: run(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
-        case 3: run(integral_constant<int, 4>{}, integral_constant<int, 3>{}); break;
-        case 9: run(integral_constant<int, 16>{}, integral_constant<int, 9>{}); break;
-        default: run(integral_constant<int, 16>{}, integral_constant<int, 0>{});   // any other K <= 16: one block per TMEM group
+    } else {
+        for (int b = g; b < nb; b += G) {
+            mbar_wait(&acc_full[b], parity);
+            __syncwarp();
+            tc_fence_after();
+            uint32_t r0[16], r1[16];
+            const uint32_t t0 = tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n);
+            tc_ld16(t0, r0);
+            tc_ld16(t0 + 16, r1);
+            tc_wait_ld();
+            uint4 lo, hi;
+            float p[K];
+            init(p);
+            epi16<2, 0>(a, r0, true, lo, hi);
+            head_fma16<K, 0>(a, lo, hi, p);
+            epi16<2, 1>(a, r1, true, lo, hi);
+            head_fma16<K, 1>(a, lo, hi, p);
+            finish(p, b);
+        }
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(e4_done);
 }
 
 }  // namespace
 
-// kHead: the level-0 decoder + head stage variant (S4 / E4); a separate instantiation, so that the other blocks' code
-// (and its instruction-cache footprint) is exactly the plain three-stage pipeline
+// kHead: the level-0 decoder + head variant (E3 differs); a separate instantiation, so that the other blocks' code --
+// and its instruction-cache footprint: measured, a head path compiled into the common kernel cost every block 3-8 % --
+// is exactly the plain three-stage pipeline
 template <int kBtEpiWarps, int kBtLoadWarps, bool kHead>
 __global__ void __launch_bounds__(bt_threads(kBtEpiWarps, kBtLoadWarps), kBtEpiWarps == 16 ? 1 : 2)
 block_tc_kernel(const __grid_constant__ BtArgs a) {
     constexpr int kBtEpiGroups = kBtEpiWarps / 4;
     constexpr int kBtThreads = bt_threads(kBtEpiWarps, kBtLoadWarps);
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *A0 = smem + a.a0_off, *A1 = smem + a.a1_off, *A2 = smem + a.a2_off, *OT = smem + a.o_off, *A3 = smem + a.a3_off;
+    uint8_t *A0 = smem + a.a0_off, *A1 = smem + a.a1_off, *A2 = smem + a.a2_off, *OT = smem + a.o_off;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.bar_off);
     // ld_full / ld_empty / tma_full exist per loader buffer: the chain of three has ONE loader buffer (A0), the chain of
     // two loads straight into the double-buffered A1
     uint64_t *ld_full = bars, *ld_empty = bars + 2, *tma_full = bars + 4, *e1_done = bars + 6, *e2_done = bars + 7, *e3_done = bars + 8;
-    uint64_t *o_free = bars + 9, *e4_done = bars + 10;
-    uint64_t *acc1_full = bars + 11, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks, *acc4_full = acc3_full + kBtMaxBlocks;
+    uint64_t *o_free = bars + 9;
+    uint64_t *acc1_full = bars + 10, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kBtNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -402,8 +393,8 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
     if (tid == 0) {
         for (int j = 0; j < 2; ++j) { mbar_init(&ld_full[j], kBtLoadWarps); mbar_init(&ld_empty[j], 1); mbar_init(&tma_full[j], 1); }
         mbar_init(o_free, 1 + (a.out_pool ? kBtLoadWarps : 0));      // store warp (+ the loader warps that pool the tile)
-        mbar_init(e1_done, kBtEpiWarps); mbar_init(e2_done, kBtEpiWarps); mbar_init(e3_done, kBtEpiWarps); mbar_init(e4_done, kBtEpiWarps);
-        for (int b = 0; b < kBtMaxBlocks; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc2_full[b], 1); mbar_init(&acc3_full[b], 1); mbar_init(&acc4_full[b], 1); }
+        mbar_init(e1_done, kBtEpiWarps); mbar_init(e2_done, kBtEpiWarps); mbar_init(e3_done, kBtEpiWarps);
+        for (int b = 0; b < kBtMaxBlocks; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc2_full[b], 1); mbar_init(&acc3_full[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kBtEpiWarps) {
@@ -508,13 +499,21 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             const uint32_t par_ = (uint32_t)(j & 1);
             if (warp == 0) BT_TL(0, j, 5);
             if constexpr (kHead) {
-                // head mode: c9 never leaves the SM -- it becomes the A operand of the head stage (flat layout, every row)
-                with_nch(a.s3.n, [&](auto nch) {
-                    epi_stage<2, decltype(nch)::value, true, kBtEpiGroups>(a, a.s3.nb, g, acc3_full, par_, (size_t)a.Pn3 * 16, [&](int b) {
-                        const int m = b * 128 + q * 32 + lane;
-                        return EpiBlk{tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, true, A3 + (size_t)m * 16};
-                    });
-                });
+                int n, y0, x0;
+                tile_coords(a, (long long)blockIdx.x + j * gridDim.x, n, y0, x0);
+                auto run = [&](auto nch, auto kk) {
+                    head_stage<decltype(nch)::value, decltype(kk)::value, kBtEpiGroups>(a, tmem, g, q, lane, acc3_full, par_, n, y0, x0);
+                };
+                using std::integral_constant;
+                const int sel = (a.s3.n >> 4) * 4 + a.head_K;                 // (channel chunks, K): fused_block_build admits 1..2 x 1..3
+                switch (sel) {
+                    case 5: run(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+                    case 6: run(integral_constant<int, 1>{}, integral_constant<int, 2>{}); break;
+                    case 7: run(integral_constant<int, 1>{}, integral_constant<int, 3>{}); break;
+                    case 9: run(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+                    case 10: run(integral_constant<int, 2>{}, integral_constant<int, 2>{}); break;
+                    default: run(integral_constant<int, 2>{}, integral_constant<int, 3>{}); break;
+                }
             } else {
             if (j >= 1) mbar_wait(o_free, (uint32_t)((j - 1) & 1));          // tile j-1 has left the staging tile
             with_nch(a.s3.n, [&](auto nch) {
@@ -528,38 +527,37 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             });
             }
             mbar_wait(&acc3_full[a.s3.nb - 1], par_);
+            if constexpr (kHead) {
+                // no shared-memory operand was written and the global stores need no ordering against the tensor core:
+                // neither the proxy fence nor a releasing arrive (both wait for the outstanding global stores)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(e3_done);
+            } else {
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(e3_done);
+            }
             if (warp == 0) BT_TL(0, j, 7);
         };
         // Schedule (see the MMA warp): while S2(i) runs, E1(i+1) fills the OTHER A1 buffer and E3(i-1) drains R3; E2(i)
         // follows S2(i) block by block.
         // With a single A1 (blocks whose weights leave no room for two) E1(i+1) must not start before S2(i) has read the
         // buffer, i.e. it follows E2(i) -- same issue order on the MMA side, less overlap.
-        // ---- E4(j): head accumulators -> probabilities / votes / class id
-        auto E4 = [&](long long j) {
-            if (warp == 0) BT_TL(0, j, 3);
-            head_epilogue<kBtEpiGroups>(a, tmem, acc4_full, e4_done, j);
-            if (warp == 0) BT_TL(0, j, 6);
-        };
         if (n_my > 0) {
+            const bool a1_double = a.a1_stride != 0;
+            if (a.has_s1) E1(0);
             if constexpr (kHead) {
-                // ONE call site per stage (prologue and tail are iterations of the same loop): the compiler inlines a lambda
-                // with a single call site whatever its size -- an out-of-line copy reads its captures and the
-                // __grid_constant__ block through memory, which doubles the instruction count of the epilogue.
-                const long long la = a.a1_stride != 0 ? 1 : 0;        // E1 runs one tile ahead when A1 is double-buffered
-                for (long long i = -1; i <= n_my + 1; ++i) {
-                    const long long e1 = i + la;
-                    if (a.has_s1 && e1 >= 0 && e1 < n_my) E1(e1);
-                    if (i >= 2) E4(i - 2);
-                    if (i >= 1 && i <= n_my) E3(i - 1);
-                    if (i >= 0 && i < n_my) E2(i);
+                // same order, but the tail E3 is an iteration of the loop: a lambda with ONE call site is inlined whatever its
+                // size -- an out-of-line E3 reads its captures and the __grid_constant__ block through memory (measured: 2x)
+                for (long long i = 0; i <= n_my; ++i) {
+                    if (a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
+                    if (i >= 1) E3(i - 1);
+                    if (i < n_my) E2(i);
+                    if (!a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
                 }
             } else {
-                const bool a1_double = a.a1_stride != 0;
-                if (a.has_s1) E1(0);
                 for (long long i = 0; i < n_my; ++i) {
                     if (a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
                     if (i >= 1) E3(i - 1);
@@ -593,7 +591,6 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         const StageRegs S1 = make_stage(a.s1, smem_u32(A0), a.Pn0);
         const StageRegs S2 = make_stage(a.s2, smem_u32(A1), a.Pn1);
         const StageRegs S3 = make_stage(a.s3, smem_u32(A2), a.Pn2);
-        const StageRegs S4 = make_stage(a.s4, smem_u32(A3), a.Pn3);
         auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
             tc_mma_f16(d, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, acc);
         };
@@ -661,39 +658,42 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             }
             __syncwarp();
         };
-        // head stage of tile j: block b accumulates into the 16-column group b / pf through the operand-B variant b % pf
-        // (its K weight columns shifted to [s*K, s*K + K), zeros elsewhere: the other blocks' columns receive += 0);
-        // per K step two MMAs, fp16 hi and lo halves of the fp32 weights
-        auto issue_s4 = [&]() {
-            if (elect_one()) {
-                const uint32_t pf = (uint32_t)a.head_pf;
-                const uint32_t slot_units = 2u * S4.ksteps * S4.b_unit;
-                uint32_t slot = 0, d = S4.d, al = S4.a_lo, bl = S4.b_lo;          // carried incrementally: no division on this path
-                auto block = [&](auto ks_tag, uint32_t b) {
-                    constexpr int KS = decltype(ks_tag)::value;
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-                        for (int j = 0; j < KS; ++j)
-                            mma(d, al + (uint32_t)j * S4.a_step, bl + (uint32_t)(hl * KS + j) * S4.b_unit, S4.idesc, (uint32_t)((hl | j) != 0) | slot);
-                    tc_commit(&acc4_full[b]);
-                    al += 128u;
-                    if (++slot == pf) { slot = 0; d += 16u; bl = S4.b_lo; } else bl += slot_units;
-                };
-                if (S4.ksteps == 1) { for (uint32_t b = 0; b < S4.nb; ++b) block(std::integral_constant<int, 1>{}, b); }
-                else if (S4.ksteps == 2) { for (uint32_t b = 0; b < S4.nb; ++b) block(std::integral_constant<int, 2>{}, b); }
-                else if (S4.ksteps == 3) { for (uint32_t b = 0; b < S4.nb; ++b) block(std::integral_constant<int, 3>{}, b); }
-                else { for (uint32_t b = 0; b < S4.nb; ++b) block(std::integral_constant<int, 4>{}, b); }
-            }
-            __syncwarp();
-        };
-        // Issue order per iteration:  S1(i+1)  [S4(i-2)]  S3(i-1)  S2(i).  The tensor pipe executes in order, so
+        // Issue order per iteration:  S1(i+1)  S3(i-1)  S2(i).  The tensor pipe executes in order, so
         //   * E1(i+1) (fills A1[(i+1)&1]) and E3(i-1) run while S2(i) (reads A1[i&1]) executes,
         //   * E2(i) starts on S2(i)'s first finished block, i.e. after S3(i-1) has stopped reading the single A2,
         //   * nothing the pipe needs next waits on an epilogue that has not been running for a whole stage already.
-        // prologue (i = -1: S1(0)) and tail (i = n_my: S4(n_my-2), S3(n_my-1); i = n_my+1: S4(n_my-1)) are iterations of the
-        // same loop, so that every issue_* lambda has one call site
-        auto issue_s2 = [&](long long i) {
+        if (a.has_s1 && n_my > 0) {
+            mbar_wait(&ld_full[0], 0);
+            tc_fence_after();
+            issue_s1();
+        }
+        for (long long i = 0; i < n_my; ++i) {
+            const uint32_t par_ = (uint32_t)(i & 1);
+            BT_TL(1, i, 0);
+            if (a.has_s1) {
+                mbar_wait(e1_done, par_);                         // A1[i&1] is complete, R1 is free
+                tc_fence_after();
+                BT_TL(1, i, 1);
+                if (i + 1 < n_my) {
+                    mbar_wait(&ld_full[0], (uint32_t)((i + 1) & 1));
+                    tc_fence_after();
+                    issue_s1();
+                }
+            }
+            BT_TL(1, i, 2);
+            if (i >= 1) {                                         // S3(i-1): A2 complete and R2 drained; R3 drained by E3(i-2)
+                mbar_wait(e2_done, par_ ^ 1u);
+                if (i >= 2) mbar_wait(e3_done, par_);
+                tc_fence_after();
+                BT_TL(1, i, 3);
+                issue_s3();
+            }
+            BT_TL(1, i, 4);
+            if (!a.has_s1) {
+                mbar_wait(&ld_full[i & 1], (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+            }
+            BT_TL(1, i, 5);
             if (elect_one()) {
                 StageRegs S2i = S2;
                 S2i.a_lo += (uint32_t)((i & 1) * a.a1_stride) >> 4;
@@ -703,97 +703,20 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 if (!a.has_s1) tc_commit(&ld_empty[i & 1]);
             }
             __syncwarp();
-        };
-        if constexpr (kHead) {
-            const long long last = n_my > 0 ? n_my + 1 : -2;
-            for (long long i = -1; i <= last; ++i) {
-                const uint32_t par_ = (uint32_t)(i & 1);
-                const bool body = i >= 0 && i < n_my;
-                if (body) BT_TL(1, i, 0);
-                if (a.has_s1) {
-                    if (body) {
-                        mbar_wait(e1_done, par_);                     // A1[i&1] is complete, R1 is free
-                        tc_fence_after();
-                        BT_TL(1, i, 1);
-                    }
-                    if (i + 1 < n_my) {
-                        mbar_wait(&ld_full[0], (uint32_t)((i + 1) & 1));
-                        tc_fence_after();
-                        issue_s1();
-                    }
-                }
-                if (body) BT_TL(1, i, 2);
-                if (i >= 1) {                                         // S3(i-1): A2 complete and R2 drained; R3 drained by E3(i-2)
-                    if (i <= n_my) mbar_wait(e2_done, par_ ^ 1u);
-                    if (i >= 2) mbar_wait(e3_done, par_);             // also: A3 of tile i-2 complete
-                    if (i >= 3) mbar_wait(e4_done, par_ ^ 1u);        // R4 drained by E4(i-3)
-                    tc_fence_after();
-                    if (body) BT_TL(1, i, 3);
-                    if (i >= 2) issue_s4();                           // S4(i-2), ahead of S3(i-1): E3(i-1) may overwrite A3 only after it
-                    if (body) BT_TL(1, i, 7);
-                    if (i <= n_my) issue_s3();
-                }
-                if (!body) continue;
-                BT_TL(1, i, 4);
-                if (!a.has_s1) {
-                    mbar_wait(&ld_full[i & 1], (uint32_t)((i >> 1) & 1));
-                    tc_fence_after();
-                }
-                BT_TL(1, i, 5);
-                issue_s2(i);
-                BT_TL(1, i, 6);
-            }
-        } else {
-            // the plain three-stage pipeline keeps the loop shape it was tuned with (measured, r2g: folding prologue and
-            // tail into the loop costs the grayscale FRONT block 6 %, and 15 % on the epilogue side)
-            if (a.has_s1 && n_my > 0) {
-                mbar_wait(&ld_full[0], 0);
-                tc_fence_after();
-                issue_s1();
-            }
-            for (long long i = 0; i < n_my; ++i) {
-                const uint32_t par_ = (uint32_t)(i & 1);
-                BT_TL(1, i, 0);
-                if (a.has_s1) {
-                    mbar_wait(e1_done, par_);                         // A1[i&1] is complete, R1 is free
-                    tc_fence_after();
-                    BT_TL(1, i, 1);
-                    if (i + 1 < n_my) {
-                        mbar_wait(&ld_full[0], (uint32_t)((i + 1) & 1));
-                        tc_fence_after();
-                        issue_s1();
-                    }
-                }
-                BT_TL(1, i, 2);
-                if (i >= 1) {                                         // S3(i-1): A2 complete and R2 drained; R3 drained by E3(i-2)
-                    mbar_wait(e2_done, par_ ^ 1u);
-                    if (i >= 2) mbar_wait(e3_done, par_);
-                    tc_fence_after();
-                    BT_TL(1, i, 3);
-                    issue_s3();
-                }
-                BT_TL(1, i, 4);
-                if (!a.has_s1) {
-                    mbar_wait(&ld_full[i & 1], (uint32_t)((i >> 1) & 1));
-                    tc_fence_after();
-                }
-                BT_TL(1, i, 5);
-                issue_s2(i);
-                BT_TL(1, i, 6);
-            }
-            if (n_my > 0) {
-                mbar_wait(e2_done, (uint32_t)((n_my - 1) & 1));
-                if (n_my >= 2) mbar_wait(e3_done, (uint32_t)((n_my - 2) & 1));
-                tc_fence_after();
-                issue_s3();
-            }
+            BT_TL(1, i, 6);
+        }
+        if (n_my > 0) {
+            mbar_wait(e2_done, (uint32_t)((n_my - 1) & 1));
+            if (n_my >= 2) mbar_wait(e3_done, (uint32_t)((n_my - 2) & 1));
+            tc_fence_after();
+            issue_s3();
         }
     } else if (warp == kBtEpiWarps + 1 + kBtLoadWarps) {
         // =====================================================================================
         //  store warp: the finished output tile leaves shared memory as one bulk copy per image row
         // =====================================================================================
         const uint32_t row_smem = (uint32_t)(a.Tw * a.s3.n * 2);
-        for (long long i = 0; i < (kHead ? 0 : n_my); ++i) {
+        for (long long i = 0; i < (kHead ? 0 : n_my); ++i) {          // head variant: nothing to ship, E3 wrote the output itself
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
             mbar_wait(e3_done, (uint32_t)(i & 1));
@@ -1110,7 +1033,7 @@ static bool bt_disabled() {
 
 static inline int round8(int v) { return (v + 7) / 8 * 8; }
 
-struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, Pn3, cols; size_t bytes; };
+struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, cols; size_t bytes; };
 
 // shared-memory / TMEM footprint of a candidate tile; plane strides are multiples of 8 positions so that every
 // plane starts 128-byte aligned (TMA destination)
@@ -1121,20 +1044,18 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
     g.nb1 = a.has_s1 ? ((th + 2) * pitch + 127) / 128 : 0;
     g.nb2 = (th * pitch + 127) / 128;
     if (g.nb1 > kBtMaxBlocks || g.nb2 > kBtMaxBlocks) return false;
-    g.cols = g.nb1 * n1 + g.nb2 * n2 + g.nb2 * n3 + (a.has_s4 ? 16 * ((g.nb2 + a.head_pf - 1) / a.head_pf) : 0);
+    g.cols = g.nb1 * n1 + g.nb2 * n2 + g.nb2 * n3;
     if (g.cols > cols_max) return false;
     if (pitch > 256 || th + 2 > 256) return false;                   // TMA box limits
     g.Pn0 = round8(g.nb1 * 128);
     g.Pn1 = round8(std::max(std::max(g.nb1 * 128, g.nb2 * 128 + 2 * pitch + 2), (th + 2) * pitch));
     g.Pn2 = round8(g.nb2 * 128);
-    g.Pn3 = g.Pn2;
     size_t off = (size_t)fb.w_bytes + (size_t)fb.par_floats * 4;
     off = (off + 127) / 128 * 128;
     if (a.has_s1) off += (size_t)g.Pn0 * (a.s1.ksteps * 2) * 16;
     off += a1_bufs * (((size_t)g.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128);
     off += (size_t)g.Pn2 * (a.s3.ksteps * 2) * 16;
-    if (a.has_s4) off += (size_t)g.Pn3 * (a.s4.ksteps * 2) * 16;             // c9 as the head stage's operand instead of the staging tile
-    else off += ((size_t)th * tw * n3 * 2 + 127) / 128 * 128;
+    if (!a.has_head) off += ((size_t)th * tw * n3 * 2 + 127) / 128 * 128;      // head variant: no output staging tile
     if (a.load_kind == 0) off += 1024;
     if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     off += (size_t)kBtNumBars * 8 + 16;
@@ -1156,7 +1077,7 @@ static double bt_best_tile(const FusedBlock &fb, int H, int W, int cols_max, siz
             if (tw > W + 1 && tw > 8) break;
             if (!bt_geom(fb, th, tw, cols_max, smem_max, a1_bufs, g)) continue;
             const double tiles = (double)((W + tw - 1) / tw) * ((H + th - 1) / th);
-            const double per_tile = (a.has_s1 ? g.nb1 * a.s1.ksteps : 0) + g.nb2 * (9.0 * a.s2.ksteps + a.s3.ksteps + (a.has_s4 ? 2.0 * a.s4.ksteps : 0.0)) + 60.0;
+            const double per_tile = (a.has_s1 ? g.nb1 * a.s1.ksteps : 0) + g.nb2 * (9.0 * a.s2.ksteps + a.s3.ksteps) + 60.0;
             const double cost = tiles * per_tile;
             if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && th * tw > bTh * bTw)) { best = cost; bTh = th; bTw = tw; }
         }
@@ -1176,7 +1097,7 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     int thd = 0, twd = 0, ths = 0, tws = 0, th2 = 0, tw2 = 0;
     const double cd = bt_best_tile(fb, H, W, 512, kBtSmemMax, 2, thd, twd);
     const double cs = a.has_s1 ? bt_best_tile(fb, H, W, 512, kBtSmemMax, 1, ths, tws) : -1.0;
-    const double c2 = a.has_s4 ? -1.0 : bt_best_tile(fb, H, W, 256, kBtSmemMax2, 2, th2, tw2);   // the head variant exists for the 1-CTA shape only
+    const double c2 = a.has_head ? -1.0 : bt_best_tile(fb, H, W, 256, kBtSmemMax2, 2, th2, tw2);   // the head variant exists for the 1-CTA shape only
     int force = 0;
     if (const char *v = getenv("IMK_BT_CTAS"); v && v[0]) force = atoi(v);
     int mode = -1;                                                    // 0: double, 1: single, 2: two CTAs
@@ -1206,18 +1127,16 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     a.tiles_x = (W + bTw - 1) / bTw; a.tiles_y = (H + bTh - 1) / bTh;
     a.s1.nb = g.nb1; a.s2.nb = a.s3.nb = g.nb2;
     a.s1.col = 0; a.s2.col = g.nb1 * (a.has_s1 ? a.s1.n : 0); a.s3.col = a.s2.col + g.nb2 * a.s2.n;
-    a.s4.nb = a.has_s4 ? g.nb2 : 0; a.s4.col = a.s3.col + g.nb2 * a.s3.n;
     a.tmem_cols = 32;
     while (a.tmem_cols < g.cols) a.tmem_cols *= 2;
-    a.Pn0 = g.Pn0; a.Pn1 = g.Pn1; a.Pn2 = g.Pn2; a.Pn3 = g.Pn3;
+    a.Pn0 = g.Pn0; a.Pn1 = g.Pn1; a.Pn2 = g.Pn2;
     size_t off = (size_t)fb.w_bytes;
     a.par_off_b = (int)off; off += (size_t)fb.par_floats * 4; off = (off + 127) / 128 * 128;
     a.a0_off = (int)off; if (a.has_s1) off += (size_t)a.Pn0 * (a.s1.ksteps * 2) * 16;
     a.a1_off = (int)off; a.a1_stride = (int)(((size_t)a.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128); off += (size_t)a1_bufs * a.a1_stride;
     if (a1_bufs == 1) a.a1_stride = 0;                               // single buffer: both parities alias
     a.a2_off = (int)off; off += (size_t)a.Pn2 * (a.s3.ksteps * 2) * 16;
-    a.o_off = a.a3_off = (int)off;
-    if (a.has_s4) off += (size_t)a.Pn3 * (a.s4.ksteps * 2) * 16; else off += ((size_t)a.Th * a.Tw * a.s3.n * 2 + 127) / 128 * 128;
+    a.o_off = (int)off; if (!a.has_head) off += ((size_t)a.Th * a.Tw * a.s3.n * 2 + 127) / 128 * 128;
     a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
     if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     a.bar_off = (int)off; off += (size_t)kBtNumBars * 8 + 16;        // everything in [a0_off, bar_off) starts zeroed
@@ -1270,6 +1189,8 @@ static int bt_upload(FusedBlock &fb, const std::vector<__half> &w, const std::ve
 // kind: 0 FRONT (L = in, conv3, conv1), 1 ENC (L = conv3, conv1), 2 DEC (L = conv1a, conv3, conv1b)
 int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned, int head_act) {
     int kind = kind_;
+    const bool head = kind == 4;
+    if (head) kind = 2;
     fb = FusedBlock{};
     if (bt_disabled()) return IMK_OK;
     if (const char *v = getenv("IMK_BT_KINDS"); v && v[0] && !((atoi(v) >> kind) & 1)) return IMK_OK;   // debug: bitmask of fused kinds
@@ -1285,8 +1206,6 @@ int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W
         if (front) pack_front_b(w, ws.data(), c.cin, c.cout, n); else pack_umma_b(w, ws.data(), c.ks, c.cin, c.cout, cin_p, n);
         s.par_off = 0;
     };
-    const bool head = kind == 4;
-    if (head) kind = 2;
     a.load_kind = kind; a.in_c = in_c;
     for (int j = (kind == 3 ? 1 : 0); j < (kind == 1 ? 2 : 3); ++j)
         if (pad_ch(L[j].cout) > 64) return IMK_OK;            // BtArgs::cpar holds 64 channels per stage
@@ -1318,28 +1237,13 @@ int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W
         stage(a.s1, L[0], kind == 0); stage(a.s2, L[1], false); stage(a.s3, L[2], false);
         a.ld_cp = kind == 0 ? 16 : pad_ch(L[0].cin);
         if (head) {
-            // S4 = the output layer (unet.py:63): 1x1, C0 -> K, no ReLU / BN; fp32 weights as fp16 hi + lo
+            // the output layer (unet.py:63): 1x1, C0 -> K, no ReLU / BN, fp32 weights -- evaluated in the E3 epilogue
             const ConvHost &o = L[3];
-            const int K = o.cout, c0p = pad_ch(o.cin);
-            if (o.ks != 1 || K < 1 || K > kBtHeadMaxK || c0p != a.s3.n) return IMK_OK;
-            const int ldw = K == 1 ? 1 : (K == 3 ? 4 : 16);          // the reference's binary heads pack several blocks per group
-            a.has_s4 = 1; a.head_K = K; a.head_ldw = ldw; a.head_pf = (16 - ldw) / K + 1; a.head_act = head_act;
-            a.s4.taps = 1; a.s4.ksteps = c0p / 16; a.s4.n = 16; a.s4.par_off = 0;
-            a.s4.w_off = (int)(w.size() * sizeof(__half));
-            // [slot][hi | lo][K step][2 planes][16 columns][8 channels]
-            const size_t base = w.size();
-            w.resize(base + (size_t)a.head_pf * 2 * a.s4.ksteps * 2 * 16 * 8, __float2half(0.f));
-            for (int s = 0; s < a.head_pf; ++s)
-                for (int hl = 0; hl < 2; ++hl)
-                    for (int ci = 0; ci < o.cin; ++ci)
-                        for (int k = 0; k < K; ++k) {
-                            const float v = o.hwio[(size_t)ci * K + k];
-                            const __half hi = __float2half_rn(v);
-                            const __half val = hl == 0 ? hi : __float2half_rn(v - __half2float(hi));
-                            const size_t unit = ((size_t)(s * 2 + hl) * a.s4.ksteps + ci / 16) * (2 * 16 * 8);
-                            w[base + unit + ((size_t)((ci % 16) / 8) * 16 + (s * K + k)) * 8 + (ci & 7)] = val;
-                        }
-            for (int k = 0; k < 16; ++k) a.hb[k] = k < K ? o.bias[k] : 0.f;
+            const int K = o.cout;
+            if (o.ks != 1 || K < 1 || K > kBtHeadMaxK || pad_ch(o.cin) != a.s3.n || a.s3.n > 32) return IMK_OK;
+            a.has_head = 1; a.head_K = K; a.head_act = head_act;
+            for (int k = 0; k < 3; ++k) for (int ci = 0; ci < 32; ++ci) a.hw[k][ci] = (k < K && ci < o.cin) ? o.hwio[(size_t)ci * K + k] : 0.f;
+            for (int k = 0; k < 4; ++k) a.hb[k] = k < K ? o.bias[k] : 0.f;
         }
     }
     if (w.size() * sizeof(__half) % 16) w.resize((w.size() + 7) / 8 * 8, __float2half(0.f));
@@ -1364,7 +1268,7 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
                        int swap_rb, int in_f32, cudaStream_t stream, const HeadOut *head) {
     BtArgs a = fb.args;
     a.in = in; a.in_lo = in_lo; a.out = out; a.swap_rb = swap_rb; a.in_f32 = in_f32;
-    if ((a.has_s4 != 0) != (head != nullptr)) { set_error("fused block: head output %s", head ? "requested from a block without a head stage" : "missing"); return IMK_EINVAL; }
+    if ((a.has_head != 0) != (head != nullptr)) { set_error("fused block: head output %s", head ? "requested from a block without a head" : "missing"); return IMK_EINVAL; }
     if (head) {
         a.head_mode = head->mode; a.head_thr = head->thr; a.head_dstar = head->dstar; a.head_strict = head->strict;
         a.head_probs = head->probs; a.head_dec = head->dec;
@@ -1401,7 +1305,7 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
         IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 3 * 16 * 8, stream));
         a.dbg = dbg_dev;
     }
-    if (a.has_s4) block_tc_kernel<16, 8, true><<<grid, bt_threads(16, 8), fb.smem, stream>>>(a);
+    if (a.has_head) block_tc_kernel<16, 8, true><<<grid, bt_threads(16, 8), fb.smem, stream>>>(a);
     else if (fb.ctas_per_sm == 2) block_tc_kernel<8, 4, false><<<grid, bt_threads(8, 4), fb.smem, stream>>>(a);
     else block_tc_kernel<16, 8, false><<<grid, bt_threads(16, 8), fb.smem, stream>>>(a);
     IMK_LAUNCHED();

@@ -6,8 +6,8 @@
 
 namespace imk {
 
-constexpr int kBtMaxBlocks = 24;
-constexpr int kBtHeadMaxK = 16;      // widest output layer the head stage takes (one 16-column TMEM group per block)        // M blocks (128 flat positions) per stage per tile
+constexpr int kBtMaxBlocks = 24;        // M blocks (128 flat positions) per stage per tile
+constexpr int kBtHeadMaxK = 3;          // widest output layer the in-epilogue head takes (on at most 32 channels)
 
 struct BtStage {
     int taps, ksteps, n, nb;            // 1|9, Cin_p/16, Cout_p (UMMA N), M blocks
@@ -48,17 +48,17 @@ struct BtArgs {
     // 256-entry table of finished fp16 rows, built in fp32 at kernel start; the loader warps copy rows straight into the
     // 3x3 stage's operand buffer: v = x/255 * fw[0][ch] + fb[ch], clamped to [flo, fhi] (BN scale folded as for the stages)
     float fw[4][32], fb[32], flo[32], fhi[32];
-    // Head stage (level-0 decoder of a network with K <= 16 outputs): S4 = the output layer `out` (unet.py:63) as a 1x1
-    // stage on the block's own c9 tile (fp16, never written to HBM), fp32 weights as fp16 hi + lo (two MMAs per K step).
-    // Accumulators of `head_pf` consecutive M blocks share one 16-column TMEM group: block b uses the operand-B variant
-    // whose K weight columns sit at [s*K, s*K + K), s = b % head_pf, and accumulates into group b / head_pf.
-    // E4 turns a pixel's K logits into (head_mode 0) fp32 probabilities [N,H,W,K], (1) a byte of threshold votes
-    // (bit k = head k fires) or (2) the argmax class id -- one byte per pixel per model instead of the c9 map.
-    int has_s4, head_K, head_pf, head_ldw, head_mode, head_act, head_strict;
+    // Head (level-0 decoder of a network with K <= 3 outputs on <= 32 channels -- the reference's binary configs):
+    // the output layer `out` (unet.py:63) runs INSIDE the last epilogue.  E3 already holds a pixel's finished c9 row
+    // (fp16 values) in registers: K * C0 fp32 FMAs with the weights as constant-bank operands give the logits
+    // (p = b; p = fma(x_c, w_c, p) in channel order, the arithmetic of the generic output kernel), the activation /
+    // decision follows in the same thread and ONE byte (or K floats) per pixel leaves the SM.  c9 is never written:
+    // no staging tile, no bulk store, no 32 B/px map in HBM.
+    // head_mode 0: fp32 probabilities [N,H,W,K] (.predict)   1: byte of threshold votes (bit k = head k fires)
+    //           2: argmax class id
+    int has_head, head_K, head_mode, head_act, head_strict;
     float head_thr, head_dstar;
-    BtStage s4;
-    int a3_off, Pn3;
-    float hb[16];
+    float hw[3][32], hb[4];
     float *head_probs;
     uint8_t *head_dec;
     int dbg_skip;                       // first tile (of CTA 0) the timeline records (IMK_BT_TL_SKIP)
@@ -74,7 +74,7 @@ struct FusedBlock {                     // one fused U-Net block of one model (d
     size_t smem = 0;
 };
 
-// What the head stage of a level-0 decoder block writes (fused_block_build kind 4)
+// What the head of a level-0 decoder block writes (fused_block_build kind 4)
 struct HeadOut {
     int mode;                           // 0: fp32 probabilities, 1: threshold votes (bit k of a byte), 2: argmax class id
     float thr, dstar;                   // mode 1: threshold; dstar > 0: the exact `1 + exp(-z) <= dstar` form of it

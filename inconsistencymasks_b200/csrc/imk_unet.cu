@@ -1033,7 +1033,12 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
                 if ((rc = fused_block_build(net->fb_enc[l], 1, &host[1 + 2 * l], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
             for (int l = 0; l < 4; ++l)
                 if ((rc = fused_block_build(net->fb_dec[l], 2, &host[11 + 3 * (3 - l)], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
-            if (getenv("IMK_BT_HEAD") && !getenv("IMK_BT_NO_HEAD") && (rc = fused_block_build(net->fb_head, 4, &host[20], d.height, d.width, 0, net->owned, d.act_out))) return fail(rc);
+            // Head-in-epilogue variant of the level-0 decoder (K <= 3): opt-in.  Measured (r2m, B200, 512 images): the block
+            // kernel is bound by the instruction issue of its epilogue warps, so the K * C0 FMAs + activation per pixel cost
+            // more there (HeLa 1107 -> 1950 us, ISIC 1150 -> 1750 us per model) than the separate ensemble_im kernel they
+            // replace (417 / 264 us per model); an MMA head stage (S4 + a fourth epilogue pass, r2c-r2h) measured the same.
+            if (const char *v = getenv("IMK_BT_HEAD"); v && v[0] == '1')
+                if ((rc = fused_block_build(net->fb_head, 4, &host[20], d.height, d.width, 0, net->owned, d.act_out))) return fail(rc);
         }
     }
     *out = net;

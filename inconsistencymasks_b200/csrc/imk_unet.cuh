@@ -37,7 +37,7 @@ struct imk_unet {
     imk::FusedBlock fb_enc[5];                  // [0] = FRONT (in + enc1), [1..3] = enc2..4, [4] = bottleneck (conv3 + conv1, no pool)
     imk::FusedBlock fb_dec[4];                  // decoder block that OUTPUTS level l
     imk::FusedBlock fb_front_u8;                // FRONT for uint8 images: input block on the loader warps, chain of two (kind 3)
-    imk::FusedBlock fb_head;                    // level-0 decoder + output layer + activation / decision (kind 4, K <= 16)
+    imk::FusedBlock fb_head;                    // level-0 decoder + output layer + activation / decision (kind 4, K <= 3 on <= 32 channels)
     std::vector<void *> owned;                  // device allocations freed at destroy
     // workspace (grown on demand), for `cap_n` images
     int64_t cap_n = 0;

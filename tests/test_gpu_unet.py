@@ -261,6 +261,46 @@ def test_fused_ensemble_equals_predict_then_im(U, F, kind, c, K, alpha, act, M):
         same(got[0], e[0]); same(got[1], e[1]); assert got[2] == e[2] and got[3] == e[3]
 
 
+@pytest.mark.parametrize("kind,c,K,alpha,act,h,w,n", [("binary", 3, 1, 0.5, "sigmoid", 32, 48, 5), ("hela", 1, 3, 1.0, "sigmoid", 256, 256, 10),
+                                                        ("binary", 3, 1, 2.0, "sigmoid", 64, 64, 4), ("multiclass", 3, 3, 1.0, "softmax", 48, 32, 4),
+                                                        ("multiclass", 3, 2, 2.0, "sigmoid", 32, 32, 3)])
+def test_head_in_epilogue_variant(U, F, monkeypatch, kind, c, K, alpha, act, h, w, n):
+    """IMK_BT_HEAD=1 (opt-in): the level-0 decoder kernel evaluates the output layer in its last epilogue and writes one
+    decision byte per pixel (ensemble_votes then only counts votes).  Same contract as the default path: .predict within
+    tolerance of the oracle, fused == predict -> reference IM arithmetic bit for bit; several tiles per CTA at 256x256."""
+    from inconsistencymasks_b200 import _lib
+    monkeypatch.setenv("IMK_BT_HEAD", "1")
+    rng = np.random.default_rng(K * 7 + h)
+    images = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    weights = [U.init_weights(c, K, alpha, seed=800 + j) for j in range(2)]
+    models = [U.B200UNet(h, w, c, K, alpha, act, wts) for wts in weights]
+    probs = [mdl.predict(images) for mdl in models]
+    same(models[0].predict(images), probs[0])
+    want = ref_unet.forward(images[:2], weights[0], act)
+    assert float(np.abs(probs[0][:2] - want).max()) <= 3e-2
+    _lib.profile_begin()
+    r = F._run_batch(models, images, kind, blank_image=images, block_input=True, block_output=True)
+    names = {p["name"] for p in _lib.profile_end()}
+    assert "block_head" in names and "ensemble_votes" in names and "ensemble_im" not in names, names
+    for i in range(n):
+        if kind == "binary":
+            lab, im, sz, pred = ref_im.im_prediction_binary([p[i] for p in probs], 0.5)
+            img_b, lab_b, _ = ref_im.blank_binary(images[i], lab, im)
+            same(r.labels[0, i], lab_b); same(r.im[i], im); same(r.image[i], img_b)
+            assert r.im_size[i] == sz and r.pred_size[0, i] == pred
+        elif kind == "hela":
+            alive, dead, pos, im, sz = ref_im.im_prediction_hela([p[i] for p in probs])
+            bf, alive_b, dead_b, _, _ = ref_im.blank_hela(images[i, ..., 0], alive, dead, np.zeros((h, w, 3), np.uint8), im)
+            same(r.labels[0, i], alive_b); same(r.labels[1, i], dead_b); same(r.labels[2, i], pos)
+            same(r.im[i], im); same(r.image[i, ..., 0], bf)
+            assert r.im_size[i] == sz
+        else:
+            lab, im, sz, _ = ref_im.im_prediction_multiclass([p[i] for p in probs])
+            img_b, lab_b, _ = ref_im.blank_multiclass(images[i], lab, im)
+            same(r.labels[0, i], lab_b); same(r.im[i], im); same(r.image[i], img_b)
+            assert r.im_size[i] == sz
+
+
 def test_fused_with_morphology_and_device_path(U, F):
     """EK / DK > 0 routes through the device-buffer calls + morphology kernels + imk_blank."""
     h, w, n, c, K = 32, 48, 4, 3, 9
