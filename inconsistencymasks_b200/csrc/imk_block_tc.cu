@@ -58,17 +58,24 @@ constexpr int kBtNumBars = 10 + 3 * kBtMaxBlocks;
 
 namespace {
 
-// timeline probe: role 0 = epilogue warp 0, 1 = MMA warp, 2 = loader warp 0 (CTA 0, 16 tiles from a.dbg_skip).
+// timeline probe: role 0 = epilogue warp 0, 1 = MMA warp, 2 = loader warp 0, 3 / 4 = issue of S1 / S3 block by block,
+// 5 = epilogue warp 5 (CTA 0, 16 tiles from a.dbg_skip).
 // Compiled in only with -DIMK_BT_TIMELINE_BUILD (IMK_BUILD_FLAGS=-DIMK_BT_TIMELINE_BUILD python -m inconsistencymasks_b200.build):
 // measured (r2l), the dormant probes alone cost the block kernels 3-9 % -- they sit on the MMA warp's issue path.
 #ifdef IMK_BT_TIMELINE_BUILD
 #define BT_TL(role, i, ev)                                                                         \
     do {                                                                                           \
         if (a.dbg && blockIdx.x == 0 && (i) >= a.dbg_skip && (i) < a.dbg_skip + 16 && (threadIdx.x & 31) == 0) \
-            a.dbg[((role) * 16 + (int)((i) - a.dbg_skip)) * 8 + (ev)] = clock64();                 \
+            a.dbg[((role) * 16 + (int)((i) - a.dbg_skip)) * 8 + ((ev) & 7)] = clock64();                 \
     } while (0)
 
+#define BT_TLX(role, i, ev)                                                                        \
+    do {                                                                                           \
+        if (a.dbg && blockIdx.x == 0 && (i) >= a.dbg_skip && (i) < a.dbg_skip + 16 && (ev) < 8)    \
+            a.dbg[((role) * 16 + (int)((i) - a.dbg_skip)) * 8 + (ev)] = clock64();                 \
+    } while (0)
 #else
+#define BT_TLX(role, i, ev) do { } while (0)
 #define BT_TL(role, i, ev) do { } while (0)
 #endif
 
@@ -114,6 +121,11 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -195,14 +207,60 @@ __device__ __forceinline__ void epi_single(const BtArgs &a, const EpiBlk &k, siz
     epi_store<STAGE, CH, PLANES>(a, r0, k, plane_bytes);
 }
 
+// 8-channel stages (BtStage::n8): accumulator columns 0..7 -> one 16-byte plane entry / output row
+template <int STAGE>
+__device__ __forceinline__ void epi8_store(const BtArgs &a, const uint32_t (&r)[8], const EpiBlk &k) {
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float v0 = __uint_as_float(r[2 * q]) + a.cpar[STAGE][2 * q];
+        const float v1 = __uint_as_float(r[2 * q + 1]) + a.cpar[STAGE][2 * q + 1];
+        __half2 h = __floats2half2_rn(v0, v1);
+        h = __hmax2(h, *reinterpret_cast<const __half2 *>(&a.clo[STAGE][q]));
+        if (a.has_hi[STAGE]) h = __hmin2(h, *reinterpret_cast<const __half2 *>(&a.chi[STAGE][q]));
+        o[q] = k.keep ? *reinterpret_cast<const uint32_t *>(&h) : 0u;
+    }
+    if (k.store) *reinterpret_cast<uint4 *>(k.dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+template <int STAGE>
+__device__ __forceinline__ void epi8_pair(const BtArgs &a, const EpiBlk &k0, const EpiBlk &k1) {
+    uint32_t r0[8], r1[8];
+    tc_ld8(k0.taddr, r0);
+    tc_ld8(k1.taddr, r1);
+    tc_wait_ld();
+    epi8_store<STAGE>(a, r0, k0);
+    epi8_store<STAGE>(a, r1, k1);
+}
+template <int STAGE>
+__device__ __forceinline__ void epi8_single(const BtArgs &a, const EpiBlk &k) {
+    uint32_t r0[8];
+    tc_ld8(k.taddr, r0);
+    tc_wait_ld();
+    epi8_store<STAGE>(a, r0, k);
+}
+
 // One epilogue stage of a warp: its M blocks are g, g + G, g + 2G, ... (G groups of four warps); `blk(b)` describes block b.
 // 16-channel stages pair two BLOCKS per wait, wider stages pair two CHUNKS of one block.
+// `cgm` = commit-group size - 1 (power of two - 1): the MMA warp commits once per group of blocks (a tcgen05.commit costs
+// tensor-pipe time), so the barrier that covers block b is the one of the group's last block
+__device__ __forceinline__ int commit_idx(int b, int cgm, int nb) { return min(b | cgm, nb - 1); }
+
 template <int STAGE, int NCH, bool PLANES, int G, typename F>
-__device__ __forceinline__ void epi_stage(const BtArgs &a, int nb, int g, uint64_t *acc_full, uint32_t parity, size_t plane_bytes, F &&blk) {
-    if constexpr (NCH == 1) {
+__device__ __forceinline__ void epi_stage(const BtArgs &a, int nb, int g, uint64_t *acc_full, uint32_t parity, size_t plane_bytes, int cgm, F &&blk) {
+    if constexpr (NCH == 0) {                                        // 8 channels: NCH = 0
         for (int b = g; b < nb; b += 2 * G) {
             const bool two = b + G < nb;                             // warp-uniform
-            mbar_wait(&acc_full[two ? b + G : b], parity);           // blocks complete in order
+            mbar_wait(&acc_full[commit_idx(two ? b + G : b, cgm, nb)], parity);
+            __syncwarp();
+            tc_fence_after();
+            const EpiBlk k0 = blk(b);
+            if (two) epi8_pair<STAGE>(a, k0, blk(b + G));
+            else epi8_single<STAGE>(a, k0);
+        }
+    } else if constexpr (NCH == 1) {
+        for (int b = g; b < nb; b += 2 * G) {
+            const bool two = b + G < nb;                             // warp-uniform
+            mbar_wait(&acc_full[commit_idx(two ? b + G : b, cgm, nb)], parity);   // blocks complete in order
             __syncwarp();
             tc_fence_after();
             const EpiBlk k0 = blk(b);
@@ -211,7 +269,7 @@ __device__ __forceinline__ void epi_stage(const BtArgs &a, int nb, int g, uint64
         }
     } else {
         for (int b = g; b < nb; b += G) {
-            mbar_wait(&acc_full[b], parity);
+            mbar_wait(&acc_full[commit_idx(b, cgm, nb)], parity);
             __syncwarp();
             tc_fence_after();
             const EpiBlk k = blk(b);
@@ -222,9 +280,11 @@ __device__ __forceinline__ void epi_stage(const BtArgs &a, int nb, int g, uint64
     }
 }
 
-template <typename F>
-__device__ __forceinline__ void with_nch(int n, F &&f) {
-    switch (n >> 4) {
+template <int NS, typename F>
+__device__ __forceinline__ void with_nch(const BtStage &st, F &&f) {
+    if constexpr (NS >= 0) { f(std::integral_constant<int, NS>{}); return; }
+    switch (st.n8 ? 0 : st.n >> 4) {
+        case 0: f(std::integral_constant<int, 0>{}); break;
         case 1: f(std::integral_constant<int, 1>{}); break;
         case 2: f(std::integral_constant<int, 2>{}); break;
         case 3: f(std::integral_constant<int, 3>{}); break;
@@ -371,10 +431,18 @@ __device__ __forceinline__ void head_stage(const BtArgs &a, uint32_t tmem, int g
 // kHead: the level-0 decoder + head variant (E3 differs); a separate instantiation, so that the other blocks' code --
 // and its instruction-cache footprint: measured, a head path compiled into the common kernel cost every block 3-8 % --
 // is exactly the plain three-stage pipeline
-template <int kBtEpiWarps, int kBtLoadWarps, bool kHead>
+// KIND = load_kind (0 FRONT, 1 ENC, 2 DEC, 3 FRONT with the input block on the loaders) and the width CLASSES of the block
+// (0: 8 channels (kin8 / n8), c >= 1: 16 c channels, -1: read at run time -- then all four are -1): CI = the loaded operand,
+// N1 / N2 / N3 = the outputs of S1 / S2 / S3 are compile-time: an instantiation holds ONE loader, ONE epilogue shape per
+// stage and ONE unrolled issue loop per stage.  Measured (ncu, r2o): the single MMA-issuing warp of the
+// all-in-one kernel (19.6k instructions) spent 22 % of its time waiting for instruction fetches and only 18 % throttled by
+// the tensor pipe -- the pipe was being starved by its own feeder.
+template <int kBtEpiWarps, int kBtLoadWarps, bool kHead, int KIND, int CI, int N1, int N2, int N3>
 __global__ void __launch_bounds__(bt_threads(kBtEpiWarps, kBtLoadWarps), kBtEpiWarps == 16 ? 1 : 2)
 block_tc_kernel(const __grid_constant__ BtArgs a) {
     constexpr int kBtEpiGroups = kBtEpiWarps / 4;
+    constexpr bool kHasS1 = KIND == 0 || KIND == 2;
+    constexpr int kIn2 = kHasS1 ? N1 : CI, kIn3 = N2;             // width class of the operand S2 / S3 read
     constexpr int kBtThreads = bt_threads(kBtEpiWarps, kBtLoadWarps);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *A0 = smem + a.a0_off, *A1 = smem + a.a1_off, *A2 = smem + a.a2_off, *OT = smem + a.o_off;
@@ -409,7 +477,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         const int zn = (a.bar_off - a.a0_off) / 16;
         for (int i = tid; i < zn; i += kBtThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
-    if (a.load_kind == 3) {                           // grayscale uint8 images only (fused_block_build)
+    if constexpr (KIND == 3) {                        // grayscale uint8 images only (fused_block_build)
         __syncthreads();                              // the table lives inside the region zeroed above
         {
             // one finished row of the input block per pixel value: [256][ld_cp] fp16
@@ -430,7 +498,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             }
         }
     }
-    if (a.load_kind == 0) {                           // x/255 as fp16 hi + lo (the same arithmetic the float path uses)
+    if constexpr (KIND == 0) {                        // x/255 as fp16 hi + lo (the same arithmetic the float path uses)
         __syncthreads();                              // the table lives inside the region zeroed above
         if (tid < 256) {
             const float xf = __fdiv_rn((float)tid, 255.0f);
@@ -458,8 +526,9 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             const uint32_t par_ = (uint32_t)(j & 1);
             uint8_t *A1j = A1 + (size_t)(j & 1) * a.a1_stride;
             if (warp == 0) BT_TL(0, j, 0);
-            with_nch(a.s1.n, [&](auto nch) {
-                epi_stage<0, decltype(nch)::value, true, kBtEpiGroups>(a, a.s1.nb, g, acc1_full, par_, (size_t)a.Pn1 * 16, [&](int b) {
+            if (warp == 5) BT_TL(5, j, 0);
+            with_nch<N1>(a.s1, [&](auto nch) {
+                epi_stage<0, decltype(nch)::value, true, kBtEpiGroups>(a, a.s1.nb, g, acc1_full, par_, (size_t)a.Pn1 * 16, a.cgm1, [&](int b) {
                     const int m = b * 128 + q * 32 + lane;
                     const int r = (int)__umulhi((unsigned)m, a.pitch_magic), c = m - r * a.pitch;
                     const int y = y0 - 1 + r, x = x0 - 1 + c;
@@ -475,13 +544,15 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(e1_done);
             if (warp == 0) BT_TL(0, j, 1);
+            if (warp == 5) BT_TL(5, j, 1);
         };
         // ---- E2(j): S2 accumulators -> ReLU -> A2 (flat layout, every row written)
         auto E2 = [&](long long j) {
             const uint32_t par_ = (uint32_t)(j & 1);
             if (warp == 0) BT_TL(0, j, 2);
-            with_nch(a.s2.n, [&](auto nch) {
-                epi_stage<1, decltype(nch)::value, true, kBtEpiGroups>(a, a.s2.nb, g, acc2_full, par_, (size_t)a.Pn2 * 16, [&](int b) {
+            if (warp == 5) BT_TL(5, j, 2);
+            with_nch<N2>(a.s2, [&](auto nch) {
+                epi_stage<1, decltype(nch)::value, true, kBtEpiGroups>(a, a.s2.nb, g, acc2_full, par_, (size_t)a.Pn2 * 16, 0, [&](int b) {
                     const int m = b * 128 + q * 32 + lane;
                     return EpiBlk{tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n), true, true, A2 + (size_t)m * 16};
                 });
@@ -492,12 +563,14 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(e2_done);
             if (warp == 0) BT_TL(0, j, 4);
+            if (warp == 5) BT_TL(5, j, 4);
         };
         // ---- E3(j): S3 accumulators -> ReLU + BN -> output tile in shared memory ([Th][Tw][C] dense); the store
         //      warp ships it with row-wise bulk copies, so no epilogue warp ever waits on a global store
         auto E3 = [&](long long j) {
             const uint32_t par_ = (uint32_t)(j & 1);
             if (warp == 0) BT_TL(0, j, 5);
+            if (warp == 5) BT_TL(5, j, 5);
             if constexpr (kHead) {
                 int n, y0, x0;
                 tile_coords(a, (long long)blockIdx.x + j * gridDim.x, n, y0, x0);
@@ -516,13 +589,13 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 }
             } else {
             if (j >= 1) mbar_wait(o_free, (uint32_t)((j - 1) & 1));          // tile j-1 has left the staging tile
-            with_nch(a.s3.n, [&](auto nch) {
-                epi_stage<2, decltype(nch)::value, false, kBtEpiGroups>(a, a.s3.nb, g, acc3_full, par_, 0, [&](int b) {
+            with_nch<N3>(a.s3, [&](auto nch) {
+                epi_stage<2, decltype(nch)::value, false, kBtEpiGroups>(a, a.s3.nb, g, acc3_full, par_, 0, a.cgm3, [&](int b) {
                     const int m = b * 128 + q * 32 + lane;
                     const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
                     const bool valid = ro < a.Th && co < a.Tw;
                     return EpiBlk{tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, valid,
-                                  OT + ((size_t)(ro * a.Tw + co) * a.s3.n) * 2};
+                                  OT + ((size_t)(ro * a.Tw + co) * a.out_c) * 2};
                 });
             });
             }
@@ -540,6 +613,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             if (lane == 0) mbar_arrive(e3_done);
             }
             if (warp == 0) BT_TL(0, j, 7);
+            if (warp == 5) BT_TL(5, j, 7);
         };
         // Schedule (see the MMA warp): while S2(i) runs, E1(i+1) fills the OTHER A1 buffer and E3(i-1) drains R3; E2(i)
         // follows S2(i) block by block.
@@ -547,22 +621,22 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         // buffer, i.e. it follows E2(i) -- same issue order on the MMA side, less overlap.
         if (n_my > 0) {
             const bool a1_double = a.a1_stride != 0;
-            if (a.has_s1) E1(0);
+            if constexpr (kHasS1) E1(0);
             if constexpr (kHead) {
                 // same order, but the tail E3 is an iteration of the loop: a lambda with ONE call site is inlined whatever its
                 // size -- an out-of-line E3 reads its captures and the __grid_constant__ block through memory (measured: 2x)
                 for (long long i = 0; i <= n_my; ++i) {
-                    if (a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
+                    if constexpr (kHasS1) { if (a1_double && i + 1 < n_my) E1(i + 1); }
                     if (i >= 1) E3(i - 1);
                     if (i < n_my) E2(i);
-                    if (!a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
+                    if constexpr (kHasS1) { if (!a1_double && i + 1 < n_my) E1(i + 1); }
                 }
             } else {
                 for (long long i = 0; i < n_my; ++i) {
-                    if (a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
+                    if constexpr (kHasS1) { if (a1_double && i + 1 < n_my) E1(i + 1); }
                     if (i >= 1) E3(i - 1);
                     E2(i);
-                    if (!a1_double && a.has_s1 && i + 1 < n_my) E1(i + 1);
+                    if constexpr (kHasS1) { if (!a1_double && i + 1 < n_my) E1(i + 1); }
                 }
                 E3(n_my - 1);
             }
@@ -576,10 +650,11 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         const uint32_t pitch = (uint32_t)a.pitch;
         // descriptor words: lo = addr >> 4 | LBO >> 4 << 16 ; hi = SBO >> 4 | version 1 << 14
         constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
-        struct StageRegs { uint32_t a_lo, a_step, b_lo, b_unit, idesc, d, n, nb, ksteps; };
+        struct StageRegs { uint32_t a_lo, a_step, b_lo, b_unit, idesc, d, n, nb, ksteps, kin8; };
         auto make_stage = [&](const BtStage &st, uint32_t abase, int Pn) {
             StageRegs r;
-            r.a_lo = (abase >> 4) | ((uint32_t)Pn << 16);            // LBO = Pn * 16 bytes
+            r.a_lo = (abase >> 4) | (st.kin8 ? 0u : (uint32_t)Pn << 16);   // LBO = Pn * 16 bytes (kin8: set per MMA, 0 for a 1x1 stage)
+            r.kin8 = (uint32_t)st.kin8;
             r.a_step = 2u * (uint32_t)Pn;                             // next K step: two 8-channel planes further
             r.b_lo = ((wbase + (uint32_t)st.w_off) >> 4) | ((uint32_t)st.n << 16);   // LBO = n * 16 bytes
             r.b_unit = (uint32_t)st.n * 2u;                           // n * 32 bytes per (tap, K step)
@@ -588,6 +663,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             r.n = (uint32_t)st.n; r.nb = (uint32_t)st.nb; r.ksteps = (uint32_t)st.ksteps;
             return r;
         };
+        const uint32_t cgm1 = (uint32_t)a.cgm1, cgm3 = (uint32_t)a.cgm3;
         const StageRegs S1 = make_stage(a.s1, smem_u32(A0), a.Pn0);
         const StageRegs S2 = make_stage(a.s2, smem_u32(A1), a.Pn1);
         const StageRegs S3 = make_stage(a.s3, smem_u32(A2), a.Pn2);
@@ -611,7 +687,14 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             constexpr int KS = decltype(ks_tag)::value;
             const uint32_t d = r.d + b * r.n;
             const uint32_t arow0 = r.a_lo + b * 128u;
-            if constexpr (KS > 0) {
+            if constexpr (KS < 0) {
+                // single 8-channel plane: K = 16 of an MMA = the 8 channels of TWO taps, LBO = the distance between them
+                mma(d, arow0 | (1u << 16), r.b_lo, r.idesc, 0u);                                              // (0,0) (0,1)
+                mma(d, (arow0 + 2u) | ((pitch - 2u) << 16), r.b_lo + r.b_unit, r.idesc, 1u);                  // (0,2) (1,0)
+                mma(d, (arow0 + pitch + 1u) | (1u << 16), r.b_lo + 2u * r.b_unit, r.idesc, 1u);               // (1,1) (1,2)
+                mma(d, (arow0 + 2u * pitch) | (1u << 16), r.b_lo + 3u * r.b_unit, r.idesc, 1u);               // (2,0) (2,1)
+                mma(d, arow0 + 2u * pitch + 2u, r.b_lo + 4u * r.b_unit, r.idesc, 1u);                         // (2,2) against zeros
+            } else if constexpr (KS > 0) {
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
                     const uint32_t arow = arow0 + (uint32_t)dy * pitch;
@@ -632,7 +715,10 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                     }
             }
         };
-        auto with_ks = [&](uint32_t ksteps, auto &&f) {
+        // K steps of a stage whose operand has width class CLS (8 channels: one step; -1: run time)
+        auto with_ks = [&](auto cls, uint32_t ksteps, auto &&f) {
+            constexpr int CLS = decltype(cls)::value;
+            if constexpr (CLS >= 0) { f(std::integral_constant<int, (CLS == 0 ? 1 : CLS)>{}); return; }
             switch (ksteps) {
                 case 1: f(std::integral_constant<int, 1>{}); break;
                 case 2: f(std::integral_constant<int, 2>{}); break;
@@ -641,19 +727,22 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 default: f(std::integral_constant<int, 0>{}); break;
             }
         };
-        auto issue_s1 = [&]() {
+        auto with_ks1 = [&](uint32_t ksteps, auto &&f) {                  // S1 of FRONT is the image stage: always one K step
+            if constexpr (KIND == 0) f(std::integral_constant<int, 1>{}); else with_ks(std::integral_constant<int, CI>{}, ksteps, f);
+        };
+        auto issue_s1 = [&](long long ti) {
             if (elect_one()) {
-                with_ks(S1.ksteps, [&](auto ks) {
-                    for (uint32_t b = 0; b < S1.nb; ++b) { block_1x1(ks, S1, b); tc_commit(&acc1_full[b]); }
+                with_ks1(S1.ksteps, [&](auto ks) {
+                    for (uint32_t b = 0; b < S1.nb; ++b) { BT_TLX(3, ti, b); block_1x1(ks, S1, b); if ((b & cgm1) == cgm1 || b + 1 == S1.nb) tc_commit(&acc1_full[b]); }
                 });
                 tc_commit(&ld_empty[0]);
             }
             __syncwarp();
         };
-        auto issue_s3 = [&]() {
+        auto issue_s3 = [&](long long ti) {
             if (elect_one()) {
-                with_ks(S3.ksteps, [&](auto ks) {
-                    for (uint32_t b = 0; b < S3.nb; ++b) { block_1x1(ks, S3, b); tc_commit(&acc3_full[b]); }
+                with_ks(std::integral_constant<int, kIn3>{}, S3.ksteps, [&](auto ks) {
+                    for (uint32_t b = 0; b < S3.nb; ++b) { BT_TLX(4, ti, b); block_1x1(ks, S3, b); if ((b & cgm3) == cgm3 || b + 1 == S3.nb) tc_commit(&acc3_full[b]); }
                 });
             }
             __syncwarp();
@@ -662,22 +751,22 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         //   * E1(i+1) (fills A1[(i+1)&1]) and E3(i-1) run while S2(i) (reads A1[i&1]) executes,
         //   * E2(i) starts on S2(i)'s first finished block, i.e. after S3(i-1) has stopped reading the single A2,
         //   * nothing the pipe needs next waits on an epilogue that has not been running for a whole stage already.
-        if (a.has_s1 && n_my > 0) {
+        if (kHasS1 && n_my > 0) {
             mbar_wait(&ld_full[0], 0);
             tc_fence_after();
-            issue_s1();
+            issue_s1(0);
         }
         for (long long i = 0; i < n_my; ++i) {
             const uint32_t par_ = (uint32_t)(i & 1);
             BT_TL(1, i, 0);
-            if (a.has_s1) {
+            if (kHasS1) {
                 mbar_wait(e1_done, par_);                         // A1[i&1] is complete, R1 is free
                 tc_fence_after();
                 BT_TL(1, i, 1);
                 if (i + 1 < n_my) {
                     mbar_wait(&ld_full[0], (uint32_t)((i + 1) & 1));
                     tc_fence_after();
-                    issue_s1();
+                    issue_s1(i + 1);
                 }
             }
             BT_TL(1, i, 2);
@@ -686,10 +775,10 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 if (i >= 2) mbar_wait(e3_done, par_);
                 tc_fence_after();
                 BT_TL(1, i, 3);
-                issue_s3();
+                issue_s3(i - 1);
             }
             BT_TL(1, i, 4);
-            if (!a.has_s1) {
+            if (!kHasS1) {
                 mbar_wait(&ld_full[i & 1], (uint32_t)((i >> 1) & 1));
                 tc_fence_after();
             }
@@ -697,10 +786,14 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             if (elect_one()) {
                 StageRegs S2i = S2;
                 S2i.a_lo += (uint32_t)((i & 1) * a.a1_stride) >> 4;
-                with_ks(S2i.ksteps, [&](auto ks) {
-                    for (uint32_t b = 0; b < S2i.nb; ++b) { block_3x3(ks, S2i, b); tc_commit(&acc2_full[b]); }
-                });
-                if (!a.has_s1) tc_commit(&ld_empty[i & 1]);
+                if (kIn2 == 0 || (kIn2 < 0 && S2i.kin8)) {
+                    for (uint32_t b = 0; b < S2i.nb; ++b) { block_3x3(std::integral_constant<int, -1>{}, S2i, b); tc_commit(&acc2_full[b]); }
+                } else if constexpr (kIn2 != 0) {
+                    with_ks(std::integral_constant<int, kIn2>{}, S2i.ksteps, [&](auto ks) {
+                        for (uint32_t b = 0; b < S2i.nb; ++b) { block_3x3(ks, S2i, b); tc_commit(&acc2_full[b]); }
+                    });
+                }
+                if (!kHasS1) tc_commit(&ld_empty[i & 1]);
             }
             __syncwarp();
             BT_TL(1, i, 6);
@@ -709,24 +802,24 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             mbar_wait(e2_done, (uint32_t)((n_my - 1) & 1));
             if (n_my >= 2) mbar_wait(e3_done, (uint32_t)((n_my - 2) & 1));
             tc_fence_after();
-            issue_s3();
+            issue_s3(n_my - 1);
         }
     } else if (warp == kBtEpiWarps + 1 + kBtLoadWarps) {
         // =====================================================================================
         //  store warp: the finished output tile leaves shared memory as one bulk copy per image row
         // =====================================================================================
-        const uint32_t row_smem = (uint32_t)(a.Tw * a.s3.n * 2);
+        const uint32_t row_smem = (uint32_t)(a.Tw * a.out_c * 2);
         for (long long i = 0; i < (kHead ? 0 : n_my); ++i) {          // head variant: nothing to ship, E3 wrote the output itself
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
             mbar_wait(e3_done, (uint32_t)(i & 1));
             if (lane == 0) {
-                const uint32_t bytes = (uint32_t)(min(a.Tw, a.W - x0) * a.s3.n * 2);
-                __half *g0 = a.out + (((long long)n * a.H + y0) * a.W + x0) * a.s3.n;
+                const uint32_t bytes = (uint32_t)(min(a.Tw, a.W - x0) * a.out_c * 2);
+                __half *g0 = a.out + (((long long)n * a.H + y0) * a.W + x0) * a.out_c;
                 const int rows = min(a.Th, a.H - y0);
                 for (int ro = 0; ro < rows; ++ro)
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(g0 + (long long)ro * a.W * a.s3.n), "r"(smem_u32(OT) + (uint32_t)ro * row_smem), "r"(bytes) : "memory");
+                                 :: "l"(g0 + (long long)ro * a.W * a.out_c), "r"(smem_u32(OT) + (uint32_t)ro * row_smem), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             __syncwarp();
@@ -744,7 +837,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         // =====================================================================================
         const int lt = tid - (kBtEpiWarps + 1) * 32;
         constexpr int NL = kBtLoadWarps * 32;
-        const int Pn = a.has_s1 ? a.Pn0 : a.Pn1;
+        const int Pn = kHasS1 ? a.Pn0 : a.Pn1;
         const int npos = (a.Th + 2) * a.pitch;
         const int KC = a.ld_cp >> 3;
         const bool first = warp == kBtEpiWarps + 1;
@@ -755,37 +848,37 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + j * gridDim.x, n, y0, x0);
             mbar_wait(e3_done, (uint32_t)(j & 1));
-            const int C8 = a.s3.n >> 3;                                   // 16-byte vectors per pixel
+            const int C8 = a.out_c >> 3;                                  // 16-byte vectors per pixel
             const int pw = min(a.Tw, a.W - x0) >> 1, ph = min(a.Th, a.H - y0) >> 1;
             const int Wp = a.W >> 1;
             const unsigned c8_magic = 0xFFFFFFFFu / (unsigned)C8 + 1u, pw_magic = 0xFFFFFFFFu / (unsigned)pw + 1u;
-            __half *p0 = a.out_pool + (((long long)n * (a.H >> 1) + (y0 >> 1)) * Wp + (x0 >> 1)) * a.s3.n;
+            __half *p0 = a.out_pool + (((long long)n * (a.H >> 1) + (y0 >> 1)) * Wp + (x0 >> 1)) * a.out_c;
             const int items = ph * pw * C8;
             for (int idx = lt; idx < items; idx += NL) {
-                const int f = (int)__umulhi((unsigned)idx, c8_magic), cv = idx - f * C8;
-                const int py = (int)__umulhi((unsigned)f, pw_magic), px = f - py * pw;
-                const uint8_t *src = OT + ((size_t)((2 * py) * a.Tw + 2 * px) * a.s3.n + cv * 8) * 2;
+                const int f = C8 == 1 ? idx : (int)__umulhi((unsigned)idx, c8_magic), cv = idx - f * C8;    // magic of 1 wraps to 0
+                const int py = pw == 1 ? f : (int)__umulhi((unsigned)f, pw_magic), px = f - py * pw;
+                const uint8_t *src = OT + ((size_t)((2 * py) * a.Tw + 2 * px) * a.out_c + cv * 8) * 2;
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(src);
-                const uint4 v1 = *reinterpret_cast<const uint4 *>(src + (size_t)a.s3.n * 2);
-                const uint4 v2 = *reinterpret_cast<const uint4 *>(src + (size_t)a.Tw * a.s3.n * 2);
-                const uint4 v3 = *reinterpret_cast<const uint4 *>(src + (size_t)(a.Tw + 1) * a.s3.n * 2);
-                *reinterpret_cast<uint4 *>(p0 + (py * Wp + px) * a.s3.n + cv * 8) = max_h8(max_h8(v0, v1), max_h8(v2, v3));
+                const uint4 v1 = *reinterpret_cast<const uint4 *>(src + (size_t)a.out_c * 2);
+                const uint4 v2 = *reinterpret_cast<const uint4 *>(src + (size_t)a.Tw * a.out_c * 2);
+                const uint4 v3 = *reinterpret_cast<const uint4 *>(src + (size_t)(a.Tw + 1) * a.out_c * 2);
+                *reinterpret_cast<uint4 *>(p0 + (py * Wp + px) * a.out_c + cv * 8) = max_h8(max_h8(v0, v1), max_h8(v2, v3));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(o_free);
         };
-        const long long pool_lag = a.has_s1 ? 3 : 2;                      // the tile whose E3 runs while this load is in flight
+        const long long pool_lag = kHasS1 ? 3 : 2;                      // the tile whose E3 runs while this load is in flight
         for (long long i = 0; i < n_my; ++i) {
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
             // chain of three: one buffer (A0), free once S1(i-1) has read it; chain of two: A1[i & 1], free once S2(i-2) has
-            const int lb = a.has_s1 ? 0 : (int)(i & 1);
-            const uint32_t lph = a.has_s1 ? (uint32_t)(i & 1) : (uint32_t)((i >> 1) & 1);
-            uint8_t *buf = a.has_s1 ? A0 : A1 + (size_t)lb * a.a1_stride;
+            const int lb = kHasS1 ? 0 : (int)(i & 1);
+            const uint32_t lph = kHasS1 ? (uint32_t)(i & 1) : (uint32_t)((i >> 1) & 1);
+            uint8_t *buf = kHasS1 ? A0 : A1 + (size_t)lb * a.a1_stride;
             if (first) BT_TL(2, i, 0);
-            if (a.has_s1 ? i >= 1 : i >= 2) mbar_wait(&ld_empty[lb], lph ^ 1u);
+            if (kHasS1 ? i >= 1 : i >= 2) mbar_wait(&ld_empty[lb], lph ^ 1u);
             if (first) BT_TL(2, i, 1);
-            if (a.load_kind == 0) {
+            if constexpr (KIND == 0) {
                 // image -> x/255 split into fp16 hi + lo so that the first layer keeps ~22 bits of the input and
                 // of the weights: K slots [hi(c) | lo(c) | hi(c)] against [w_hi | w_hi | w_lo]
                 const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem + a.lut_off);
@@ -857,7 +950,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                         *reinterpret_cast<uint4 *>(buf + ((size_t)Pn + f) * 16) = reinterpret_cast<const uint4 *>(v)[1];
                     }
                 }
-            } else if (a.load_kind == 3) {
+            } else if constexpr (KIND == 3) {
                 // input block through the table: a grayscale uint8 pixel selects the finished fp16 row of the 3x3 stage's
                 // operand (zero outside the image: Conv2D 'same' pads the map the 3x3 reads, unet.py:12)
                 const uint8_t *img = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.H * a.W;
@@ -884,7 +977,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                         }
                     }
                 }
-            } else if (a.load_kind == 1) {
+            } else if constexpr (KIND == 1) {
                 // the haloed tile: one TMA box per 8-channel plane, zero filled outside the image
                 if (first && elect_one()) {
                     mbar_expect_tx(&tma_full[lb], (uint32_t)KC * 16u * (uint32_t)npos);
@@ -919,7 +1012,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
 #pragma unroll
                     for (int k = 0; k < PB; ++k) {
                         const int idx = i0 + k * NL;
-                        const int f = (int)__umulhi((unsigned)idx, kc_magic), kc = idx - f * KC;
+                        const int f = KC == 1 ? idx : (int)__umulhi((unsigned)idx, kc_magic), kc = idx - f * KC;   // magic of 1 wraps to 0
                         const int r = (int)__umulhi((unsigned)f, pl_magic), c = f - r * pl;
                         const int yl = yl0 + r, xl = xl0 + c;
                         const bool ok = idx < n_items && yl >= 0 && yl < Hl && xl >= 0 && xl < Wl;
@@ -972,6 +1065,35 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
 // =============================================================================================
 //  host side
 // =============================================================================================
+typedef void (*BtKernel)(const BtArgs);
+// The instantiation for a launch shape (two: the 2-CTA/SM shape, run-time widths only), a load kind and the width
+// classes (ci | n1 | n2 | n3, -1 where the kind has no such operand / stage).  The table holds the shapes U-Nets of
+// unet.py produce -- FRONT: (c, c, c); ENC: c -> (2c, 2c); DEC: c -> (c, c, c) at level 0, (c, c, c/2) above -- for the
+// widths the resident-weight design admits; anything else takes the run-time instantiation of its kind.
+static BtKernel bt_kernel(bool two, int kind, int ci, int n1, int n2, int n3) {
+    if (two) {
+        switch (kind) {
+            case 0: return block_tc_kernel<8, 4, false, 0, -1, -1, -1, -1>;
+            case 1: return block_tc_kernel<8, 4, false, 1, -1, -1, -1, -1>;
+            case 2: return block_tc_kernel<8, 4, false, 2, -1, -1, -1, -1>;
+            default: return block_tc_kernel<8, 4, false, 3, -1, -1, -1, -1>;
+        }
+    }
+#define IMK_BT_IS(K, A, B, C, D) if (kind == K && ci == A && n1 == B && n2 == C && n3 == D) return block_tc_kernel<16, 8, false, K, A, B, C, D>
+    IMK_BT_IS(0, -1, 0, 0, 0); IMK_BT_IS(0, -1, 1, 1, 1); IMK_BT_IS(0, -1, 2, 2, 2);               // FRONT, image stage on the tensor cores
+    IMK_BT_IS(3, 0, -1, 0, 0); IMK_BT_IS(3, 1, -1, 1, 1); IMK_BT_IS(3, 2, -1, 2, 2);               // FRONT, input block on the loaders
+    IMK_BT_IS(1, 0, -1, 1, 1); IMK_BT_IS(1, 1, -1, 2, 2); IMK_BT_IS(1, 2, -1, 4, 4);               // ENC: c -> 2c
+    IMK_BT_IS(2, 0, 0, 0, 0); IMK_BT_IS(2, 1, 1, 1, 1); IMK_BT_IS(2, 2, 2, 2, 2);                  // DEC level 0
+    IMK_BT_IS(2, 1, 1, 1, 0); IMK_BT_IS(2, 2, 2, 2, 1); IMK_BT_IS(2, 4, 4, 4, 2);                  // DEC above: c -> c/2
+#undef IMK_BT_IS
+    switch (kind) {
+        case 0: return block_tc_kernel<16, 8, false, 0, -1, -1, -1, -1>;
+        case 1: return block_tc_kernel<16, 8, false, 1, -1, -1, -1, -1>;
+        case 2: return block_tc_kernel<16, 8, false, 2, -1, -1, -1, -1>;
+        default: return block_tc_kernel<16, 8, false, 3, -1, -1, -1, -1>;
+    }
+}
+
 static void pack_umma_b(std::vector<__half> &dst, const float *hwio, int ks, int cin, int cout, int cin_p, int cout_p) {
     // [tap][kc = cin_p/8][cout_p][8] fp16, zero in the padding (the operand-B image of imk_conv_tc.cu)
     const int taps = ks * ks, KC = cin_p / 8;
@@ -981,6 +1103,19 @@ static void pack_umma_b(std::vector<__half> &dst, const float *hwio, int ks, int
         for (int ci = 0; ci < cin; ++ci)
             for (int co = 0; co < cout; ++co)
                 dst[base + (((size_t)tap * KC + ci / 8) * cout_p + co) * 8 + (ci & 7)] =
+                    __float2half_rn(hwio[((size_t)tap * cin + ci) * cout + co]);
+}
+
+// operand B of a stage whose A operand is ONE 8-channel plane (BtStage::kin8): images of [2 kc][cout_p][8] fp16.
+// 3x3: five images, image j = taps (2j, 2j + 1) stacked along K (zeros under the ninth tap); 1x1: one image, zeros in kc 1.
+static void pack_umma_b8(std::vector<__half> &dst, const float *hwio, int ks, int cin, int cout, int cout_p) {
+    const int taps = ks * ks, imgs = (taps + 1) / 2;
+    const size_t base = dst.size();
+    dst.resize(base + (size_t)imgs * 2 * cout_p * 8, __float2half(0.f));
+    for (int tap = 0; tap < taps; ++tap)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int co = 0; co < cout; ++co)
+                dst[base + (((size_t)(tap / 2) * 2 + (tap & 1)) * cout_p + co) * 8 + ci] =
                     __float2half_rn(hwio[((size_t)tap * cin + ci) * cout + co]);
 }
 
@@ -1034,6 +1169,7 @@ static bool bt_disabled() {
 static inline int round8(int v) { return (v + 7) / 8 * 8; }
 
 struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, cols; size_t bytes; };
+static inline int bt_planes(const BtStage &st) { return st.kin8 ? 1 : st.ksteps * 2; }     // 16-byte planes of the stage's A operand
 
 // shared-memory / TMEM footprint of a candidate tile; plane strides are multiples of 8 positions so that every
 // plane starts 128-byte aligned (TMA destination)
@@ -1041,6 +1177,7 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
     const BtArgs &a = fb.args;
     const int pitch = tw + 2;
     const int n1 = a.has_s1 ? a.s1.n : 0, n2 = a.s2.n, n3 = a.s3.n;
+    (void)n3;
     g.nb1 = a.has_s1 ? ((th + 2) * pitch + 127) / 128 : 0;
     g.nb2 = (th * pitch + 127) / 128;
     if (g.nb1 > kBtMaxBlocks || g.nb2 > kBtMaxBlocks) return false;
@@ -1052,10 +1189,10 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
     g.Pn2 = round8(g.nb2 * 128);
     size_t off = (size_t)fb.w_bytes + (size_t)fb.par_floats * 4;
     off = (off + 127) / 128 * 128;
-    if (a.has_s1) off += (size_t)g.Pn0 * (a.s1.ksteps * 2) * 16;
-    off += a1_bufs * (((size_t)g.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128);
-    off += (size_t)g.Pn2 * (a.s3.ksteps * 2) * 16;
-    if (!a.has_head) off += ((size_t)th * tw * n3 * 2 + 127) / 128 * 128;      // head variant: no output staging tile
+    if (a.has_s1) off += (size_t)g.Pn0 * bt_planes(a.s1) * 16;
+    off += a1_bufs * (((size_t)g.Pn1 * bt_planes(a.s2) * 16 + 127) / 128 * 128);
+    off += (size_t)g.Pn2 * bt_planes(a.s3) * 16;
+    if (!a.has_head) off += ((size_t)th * tw * a.out_c * 2 + 127) / 128 * 128;  // head variant: no output staging tile
     if (a.load_kind == 0) off += 1024;
     if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     off += (size_t)kBtNumBars * 8 + 16;
@@ -1077,7 +1214,7 @@ static double bt_best_tile(const FusedBlock &fb, int H, int W, int cols_max, siz
             if (tw > W + 1 && tw > 8) break;
             if (!bt_geom(fb, th, tw, cols_max, smem_max, a1_bufs, g)) continue;
             const double tiles = (double)((W + tw - 1) / tw) * ((H + th - 1) / th);
-            const double per_tile = (a.has_s1 ? g.nb1 * a.s1.ksteps : 0) + g.nb2 * (9.0 * a.s2.ksteps + a.s3.ksteps) + 60.0;
+            const double per_tile = (a.has_s1 ? g.nb1 * a.s1.ksteps : 0) + g.nb2 * ((a.s2.kin8 ? 5.0 : 9.0 * a.s2.ksteps) + a.s3.ksteps) + 60.0;
             const double cost = tiles * per_tile;
             if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && th * tw > bTh * bTw)) { best = cost; bTh = th; bTw = tw; }
         }
@@ -1132,11 +1269,11 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     a.Pn0 = g.Pn0; a.Pn1 = g.Pn1; a.Pn2 = g.Pn2;
     size_t off = (size_t)fb.w_bytes;
     a.par_off_b = (int)off; off += (size_t)fb.par_floats * 4; off = (off + 127) / 128 * 128;
-    a.a0_off = (int)off; if (a.has_s1) off += (size_t)a.Pn0 * (a.s1.ksteps * 2) * 16;
-    a.a1_off = (int)off; a.a1_stride = (int)(((size_t)a.Pn1 * (a.s2.ksteps * 2) * 16 + 127) / 128 * 128); off += (size_t)a1_bufs * a.a1_stride;
+    a.a0_off = (int)off; if (a.has_s1) off += (size_t)a.Pn0 * bt_planes(a.s1) * 16;
+    a.a1_off = (int)off; a.a1_stride = (int)(((size_t)a.Pn1 * bt_planes(a.s2) * 16 + 127) / 128 * 128); off += (size_t)a1_bufs * a.a1_stride;
     if (a1_bufs == 1) a.a1_stride = 0;                               // single buffer: both parities alias
-    a.a2_off = (int)off; off += (size_t)a.Pn2 * (a.s3.ksteps * 2) * 16;
-    a.o_off = (int)off; if (!a.has_head) off += ((size_t)a.Th * a.Tw * a.s3.n * 2 + 127) / 128 * 128;
+    a.a2_off = (int)off; off += (size_t)a.Pn2 * bt_planes(a.s3) * 16;
+    a.o_off = (int)off; if (!a.has_head) off += ((size_t)a.Th * a.Tw * a.out_c * 2 + 127) / 128 * 128;
     a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
     if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     a.bar_off = (int)off; off += (size_t)kBtNumBars * 8 + 16;        // everything in [a0_off, bar_off) starts zeroed
@@ -1187,7 +1324,7 @@ static int bt_upload(FusedBlock &fb, const std::vector<__half> &w, const std::ve
 }
 
 // kind: 0 FRONT (L = in, conv3, conv1), 1 ENC (L = conv3, conv1), 2 DEC (L = conv1a, conv3, conv1b)
-int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned, int head_act) {
+int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned, int head_act, bool allow8) {
     int kind = kind_;
     const bool head = kind == 4;
     if (head) kind = 2;
@@ -1199,11 +1336,15 @@ int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W
     std::vector<float> par(4, 0.f);
     auto stage = [&](BtStage &s, const ConvHost &c, bool front) {
         const int cin_p = front ? 16 : pad_ch(c.cin), n = pad_ch(c.cout);
+        s.kin8 = (allow8 && !front && c.cin <= 8) ? 1 : 0;
+        s.n8 = (allow8 && c.cout <= 8) ? 1 : 0;
         s.taps = front ? 1 : c.ks * c.ks; s.ksteps = cin_p / 16; s.n = n;
         s.w_off = (int)(w.size() * sizeof(__half));
         const int si = &s == &a.s1 ? 0 : (&s == &a.s2 ? 1 : 2);
         const std::vector<float> ws = fold_stage(c, a, si);
-        if (front) pack_front_b(w, ws.data(), c.cin, c.cout, n); else pack_umma_b(w, ws.data(), c.ks, c.cin, c.cout, cin_p, n);
+        if (front) pack_front_b(w, ws.data(), c.cin, c.cout, n);
+        else if (s.kin8) pack_umma_b8(w, ws.data(), c.ks, c.cin, c.cout, n);
+        else pack_umma_b(w, ws.data(), c.ks, c.cin, c.cout, cin_p, n);
         s.par_off = 0;
     };
     a.load_kind = kind; a.in_c = in_c;
@@ -1215,7 +1356,7 @@ int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W
         if (L[0].ks != 1 || L[1].ks != 3 || L[2].ks != 1 || in_c != 1 || pad_ch(L[0].cout) > 32) return IMK_OK;
         a.has_s1 = 0;
         stage(a.s2, L[1], false); stage(a.s3, L[2], false);
-        a.ld_cp = pad_ch(L[0].cout);
+        a.ld_cp = a.s2.kin8 ? 8 : pad_ch(L[0].cout);
         const float inf = INFINITY;
         for (int ch = 0; ch < 32; ++ch) { for (int c = 0; c < 4; ++c) a.fw[c][ch] = 0.f; a.fb[ch] = 0.f; a.flo[ch] = 0.f; a.fhi[ch] = inf; }
         for (int co = 0; co < L[0].cout; ++co) {
@@ -1229,23 +1370,24 @@ int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W
         if (L[0].ks != 3 || L[1].ks != 1) return IMK_OK;
         a.has_s1 = 0;
         stage(a.s2, L[0], false); stage(a.s3, L[1], false);
-        a.ld_cp = pad_ch(L[0].cin);
+        a.ld_cp = a.s2.kin8 ? 8 : pad_ch(L[0].cin);
     } else {
         if (L[0].ks != 1 || L[1].ks != 3 || L[2].ks != 1) return IMK_OK;
         if (kind == 0 && 3 * in_c > 16) return IMK_OK;
         a.has_s1 = 1;
         stage(a.s1, L[0], kind == 0); stage(a.s2, L[1], false); stage(a.s3, L[2], false);
-        a.ld_cp = kind == 0 ? 16 : pad_ch(L[0].cin);
+        a.ld_cp = kind == 0 ? 16 : (a.s1.kin8 ? 8 : pad_ch(L[0].cin));
         if (head) {
             // the output layer (unet.py:63): 1x1, C0 -> K, no ReLU / BN, fp32 weights -- evaluated in the E3 epilogue
             const ConvHost &o = L[3];
             const int K = o.cout;
-            if (o.ks != 1 || K < 1 || K > kBtHeadMaxK || pad_ch(o.cin) != a.s3.n || a.s3.n > 32) return IMK_OK;
+            if (o.ks != 1 || K < 1 || K > kBtHeadMaxK || pad_ch(o.cin) != a.s3.n || a.s3.n > 32 || a.s3.n8) return IMK_OK;
             a.has_head = 1; a.head_K = K; a.head_act = head_act;
             for (int k = 0; k < 3; ++k) for (int ci = 0; ci < 32; ++ci) a.hw[k][ci] = (k < K && ci < o.cin) ? o.hwio[(size_t)ci * K + k] : 0.f;
             for (int k = 0; k < 4; ++k) a.hb[k] = k < K ? o.bias[k] : 0.f;
         }
     }
+    a.out_c = a.s3.n8 ? 8 : a.s3.n;
     if (w.size() * sizeof(__half) % 16) w.resize((w.size() + 7) / 8 * 8, __float2half(0.f));
     fb.w_bytes = a.w_bytes = (int)(w.size() * sizeof(__half));
     fb.par_floats = a.par_floats = (int)par.size();
@@ -1274,6 +1416,15 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
         a.head_probs = head->probs; a.head_dec = head->dec;
         if ((head->mode == 0 && !head->probs) || (head->mode != 0 && !head->dec)) { set_error("fused block: NULL head output"); return IMK_EINVAL; }
     }
+    {   // commit groups of the 1x1 stages (IMK_BT_CG1 / IMK_BT_CG3 = 1, 2, 4, 8 blocks per tcgen05.commit)
+        static int cg1 = -1, cg3 = -1;
+        if (cg1 < 0) {
+            auto rd = [](const char *name, int dflt) { const char *v = getenv(name); const int x = v && v[0] ? atoi(v) : dflt; return (x == 2 || x == 4 || x == 8) ? x - 1 : 0; };
+            cg3 = rd("IMK_BT_CG3", 1);
+            cg1 = rd("IMK_BT_CG1", 1);
+        }
+        a.cgm1 = cg1; a.cgm3 = a.has_head ? 0 : cg3;
+    }
     a.out_pool = out_pool;
     if (out_pool && !fused_block_can_pool(fb)) { set_error("fused block: the tile cannot carry the 2x2 max-pool"); return IMK_EINVAL; }
     a.n_tiles = (long long)n * a.tiles_x * a.tiles_y;
@@ -1282,18 +1433,21 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
         int rc = make_map(&a.tm_in, in, n, a.H, a.W, a.ld_cp, a.pitch, a.Th + 2);
         if (rc) return rc;
     }
-    // the opt-in is per device (a process may drive several GPUs): once per device, not per launch
+    // width classes of the block (see bt_kernel)
+    int ci = -1, n1 = -1, n2 = -1, n3 = -1;
     {
-        static bool attr_set[64] = {false};
-        int dev = 0;
-        IMK_CUDA(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-            IMK_CUDA(cudaFuncSetAttribute(block_tc_kernel<16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmemMax));
-            IMK_CUDA(cudaFuncSetAttribute(block_tc_kernel<16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmemMax));
-            IMK_CUDA(cudaFuncSetAttribute(block_tc_kernel<8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtSmemMax2));
-            if (dev >= 0 && dev < 64) attr_set[dev] = true;
-        }
+        auto out_cls = [](const BtStage &st) { return st.n8 ? 0 : st.n >> 4; };
+        auto in_cls = [](const BtStage &st) { return st.kin8 ? 0 : st.ksteps; };
+        n2 = out_cls(a.s2); n3 = out_cls(a.s3);
+        if (a.has_s1) { n1 = out_cls(a.s1); ci = a.load_kind == 0 ? -1 : in_cls(a.s1); }
+        else ci = in_cls(a.s2);
+        if (a.s2.n % 16 || a.s3.n % 16 || (a.has_s1 && a.s1.n % 16)) ci = -9;          // no such instantiation
+        if (const char *v = getenv("IMK_BT_GENERIC"); v && v[0] == '1') ci = -9;
     }
+    const BtKernel kern = a.has_head ? (BtKernel)block_tc_kernel<16, 8, true, 2, -1, -1, -1, -1>
+                                     : bt_kernel(fb.ctas_per_sm == 2, a.load_kind, ci, n1, n2, n3);
+    // the opt-in is per device (a process may drive several GPUs) and per instantiation: cheap, so set at every launch
+    IMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fb.ctas_per_sm == 2 ? kBtSmemMax2 : kBtSmemMax));
     const int grid = (int)std::min<long long>(a.n_tiles, (long long)num_sms() * fb.ctas_per_sm);
     static long long *dbg_dev = nullptr;
     const char *tl = getenv("IMK_BT_TIMELINE");
@@ -1301,23 +1455,21 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
     a.dbg_skip = 0;
     if (const char *v = getenv("IMK_BT_TL_SKIP"); v && v[0]) a.dbg_skip = atoi(v);
     if (tl && tl[0] == '1') {
-        if (!dbg_dev) IMK_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 3 * 16 * 8));
-        IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 3 * 16 * 8, stream));
+        if (!dbg_dev) IMK_CUDA(cudaMalloc(&dbg_dev, sizeof(long long) * 6 * 16 * 8));
+        IMK_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 6 * 16 * 8, stream));
         a.dbg = dbg_dev;
     }
-    if (a.has_head) block_tc_kernel<16, 8, true><<<grid, bt_threads(16, 8), fb.smem, stream>>>(a);
-    else if (fb.ctas_per_sm == 2) block_tc_kernel<8, 4, false><<<grid, bt_threads(8, 4), fb.smem, stream>>>(a);
-    else block_tc_kernel<16, 8, false><<<grid, bt_threads(16, 8), fb.smem, stream>>>(a);
+    kern<<<grid, fb.ctas_per_sm == 2 ? bt_threads(8, 4) : bt_threads(16, 8), fb.smem, stream>>>(a);
     IMK_LAUNCHED();
     if (a.dbg) {
-        long long h[3 * 16 * 8];
+        long long h[6 * 16 * 8];
         IMK_CUDA(cudaStreamSynchronize(stream));
         IMK_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
         long long t0 = 0;
         for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
         fprintf(stderr, "[imk] timeline kind=%d %dx%d tile %dx%d (cycles since first event; rows: tile, cols: events)\n", a.load_kind, a.H, a.W, a.Th, a.Tw);
-        const char *names[3] = {"epi ", "mma ", "load"};
-        for (int r = 0; r < 3; ++r)
+        const char *names[6] = {"epi ", "mma ", "load", "s1is", "s3is", "epi5"};
+        for (int r = 0; r < 6; ++r)
             for (int i = 0; i < 8; ++i) {
                 fprintf(stderr, "[imk]   %s t%d:", names[r], i);
                 for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", h[(r * 16 + i) * 8 + e] ? h[(r * 16 + i) * 8 + e] - t0 : -1);

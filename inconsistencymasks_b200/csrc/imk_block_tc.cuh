@@ -14,6 +14,13 @@ struct BtStage {
     int w_off;                          // byte offset of [tap][kstep][2][n][8] fp16 in the weight region
     int par_off;                        // float offset of bias[n] | scale[n] | shift[n]
     int col;                            // first TMEM column of the stage's accumulator region
+    // 8-channel maps (int(16 * alpha) <= 8, the reference's alpha = 0.5 networks) keep ONE 16-byte plane per position:
+    //   kin8: the stage's A operand is a single plane.  K = 16 of an MMA then spans TWO positions: the descriptor's
+    //         leading-dimension offset is the distance between two TAPS (f, f + 1: LBO = 16 bytes; (0,2) -> (1,0):
+    //         LBO = (pitch - 2) * 16), so a 3x3 stage is 5 MMAs instead of 9 (operand B = the two taps' weights stacked,
+    //         zeros under the odd tap); a 1x1 stage reads its plane twice (LBO = 0) against zero weights in the second chunk
+    //   n8:   only accumulator columns 0..7 are real (UMMA N stays 16): the epilogue loads 8 columns and writes one plane
+    int kin8, n8;
 };
 
 struct BtArgs {
@@ -35,7 +42,8 @@ struct BtArgs {
     int a1_stride;                      // A1 is double-buffered (tile parity): bytes between the two copies
     unsigned pitch_magic;               // ceil(2^32 / pitch)
     int tmem_cols;                      // TMEM columns to allocate (power of two >= the three accumulator regions)
-    int o_off;                          // output staging tile [Th][Tw][Cout] fp16
+    int o_off;                          // output staging tile [Th][Tw][out_c] fp16
+    int out_c;                          // channels per pixel of the output map in HBM (s3.n, or 8 when s3.n8)
     int lut_off;                        // FRONT: 256-entry table of x/255 as fp16 hi | lo << 16
     alignas(64) CUtensorMap tm_in;      // TMA map (ENC / DEC): {8 ch, pitch, Th + 2, 1} boxes of the fp16 NHWC input / skip map
     // Epilogue constants, read as constant-bank operands (no loads): the BN scale is folded into the weights, so a
@@ -61,6 +69,7 @@ struct BtArgs {
     float hw[3][32], hb[4];
     float *head_probs;
     uint8_t *head_dec;
+    int cgm1, cgm3;                     // commit-group size - 1 of the 1x1 stages (see commit_idx)
     int dbg_skip;                       // first tile (of CTA 0) the timeline records (IMK_BT_TL_SKIP)
     long long *dbg;                     // optional timeline buffer (IMK_BT_TIMELINE=1): [3 roles][16 tiles][8 events] clocks of CTA 0
 };
@@ -96,7 +105,9 @@ int make_map(CUtensorMap *map, const void *base, int64_t n, int h, int w, int c,
 //       3 FRONT for uint8 images with the input block computed by the loader (a chain of two),
 //       4 DEC + head (conv1a, conv3, conv1b, out): L[3] is the output layer, `head_act` its activation.
 // Leaves fb.ok == false (and returns IMK_OK) when the block does not fit the resident-weight design.
-int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned, int head_act = 0);
+// allow8: maps of <= 8 channels are stored / staged as ONE 8-channel plane (BtStage::kin8 / n8); every producer and
+// consumer of such a map must then be a fused block built with allow8 (imk_unet_create checks this).
+int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W, int in_c, std::vector<void *> &owned, int head_act = 0, bool allow8 = false);
 // out_pool (optional, needs fused_block_can_pool): the 2x2 max-pooled map is written next to `out` by the same kernel.
 bool fused_block_can_pool(const FusedBlock &fb);
 int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo, __half *out, __half *out_pool, int64_t n,

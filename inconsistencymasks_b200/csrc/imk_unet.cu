@@ -810,10 +810,11 @@ int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int
     const int64_t px0 = n * d.height * d.width;
     const bool fused = net->engine == 2;
     auto pool = [&](int l) -> const __half * {                     // MaxPooling2D of lvl[l].skip -> next level's input
-        const int64_t items = n * (lv[l].h / 2) * (lv[l].w / 2) * (lv[l].ch_p / 8);
+        const int chp = (fused && net->c8 && net->widths[l] <= 8) ? 8 : lv[l].ch_p;   // 8-channel maps keep one plane (BtStage::n8)
+        const int64_t items = n * (lv[l].h / 2) * (lv[l].w / 2) * (chp / 8);
         __half *pooled = (l < 3) ? lv[l + 1].b : lv[4].a;
         IMK_PROFILE("maxpool", -1, stream);
-        maxpool_kernel<<<grid_1d(items), 256, 0, stream>>>(lv[l].skip, pooled, n, lv[l].h, lv[l].w, lv[l].ch_p);
+        maxpool_kernel<<<grid_1d(items), 256, 0, stream>>>(lv[l].skip, pooled, n, lv[l].h, lv[l].w, chp);
         ++launch_counter();
         return pooled;
     };
@@ -914,14 +915,15 @@ static int launch_out_probs(imk_unet *net, int64_t n, float *probs, cudaStream_t
     const imk_unet_desc &d = net->desc;
     const ConvLayer &Lo = net->conv.back();
     const int64_t px = n * d.height * d.width;
-    const int K = d.num_outputmasks, c1p = Lo.cin_p;
+    const int K = d.num_outputmasks, c1p = unet_c9_channels(net);
+    const float *w_out = unet_out_weights(net);
     return dispatch_head(K, c1p, [&](auto kmax, auto kfix, auto c1fix) -> int {
         constexpr int KM = decltype(kmax)::value, KF = decltype(kfix)::value, CF = decltype(c1fix)::value;
         size_t smem = (size_t)((K * c1p + K + 3) / 4 * 4) * sizeof(float);
         if constexpr (KF > 0) smem += (size_t)HeadMma<KF, CF>::BFRAG_WORDS * 4 + 8 * (size_t)HeadMma<KF, CF>::WARP_BYTES;
         IMK_CUDA(cudaFuncSetAttribute(out_probs_kernel<KM, KF, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         IMK_PROFILE("out_probs", 23, stream);
-        out_probs_kernel<KM, KF, CF><<<grid_1d(px, 256, 4), 256, smem, stream>>>(net->lvl[0].a, c1p, Lo.w_f32, Lo.bias, K, d.act_out, probs, px);
+        out_probs_kernel<KM, KF, CF><<<grid_1d(px, 256, 4), 256, smem, stream>>>(net->lvl[0].a, c1p, w_out, Lo.bias, K, d.act_out, probs, px);
         IMK_LAUNCHED();
         return IMK_OK;
     });
@@ -985,6 +987,12 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
                 for (int ci = 0; ci < it.cin; ++ci)
                     for (int co = 0; co < it.cout; ++co) wf[(size_t)co * L.cin_p + ci] = k[(size_t)ci * it.cout + co];
                 if ((rc = upload(net->owned, wf, &L.w_f32))) return fail(rc);
+                if (it.cin <= 8) {                                              // c9 as ONE 8-channel plane (imk_unet::c8): [K][8]
+                    std::vector<float> w8((size_t)it.cout * 8, 0.f);
+                    for (int ci = 0; ci < it.cin; ++ci)
+                        for (int co = 0; co < it.cout; ++co) w8[(size_t)co * 8 + ci] = k[(size_t)ci * it.cout + co];
+                    if ((rc = upload(net->owned, w8, &net->w_out8))) return fail(rc);
+                }
             } else {
                 std::vector<__half> wh((size_t)it.ks * it.ks * L.cin_p * L.cout_p, __float2half(0.f));
                 for (int tap = 0; tap < it.ks * it.ks; ++tap)
@@ -1027,17 +1035,39 @@ extern "C" int imk_unet_create(const imk_unet_desc *desc, const float *const *we
         for (size_t ci = 0; ci < host.size(); ++ci)
             if (net->conv[ci].has_bn) { host[ci].bn_scale = host_bn[bi].data(); host[ci].bn_shift = host_bn[bi + 1].data(); bi += 2; }
         if (d.ks == 3) {
-            if ((rc = fused_block_build(net->fb_enc[0], 0, &host[0], d.height, d.width, d.in_channels, net->owned))) return fail(rc);
-            if (!getenv("IMK_BT_NO_FRONT_U8") && (rc = fused_block_build(net->fb_front_u8, 3, &host[0], d.height, d.width, d.in_channels, net->owned))) return fail(rc);
-            for (int l = 1; l < 5; ++l)
-                if ((rc = fused_block_build(net->fb_enc[l], 1, &host[1 + 2 * l], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
-            for (int l = 0; l < 4; ++l)
-                if ((rc = fused_block_build(net->fb_dec[l], 2, &host[11 + 3 * (3 - l)], d.height >> l, d.width >> l, 0, net->owned))) return fail(rc);
+            auto build_all = [&](bool allow8) -> int {
+                int r;
+                if ((r = fused_block_build(net->fb_enc[0], 0, &host[0], d.height, d.width, d.in_channels, net->owned, 0, allow8))) return r;
+                if (!getenv("IMK_BT_NO_FRONT_U8") && (r = fused_block_build(net->fb_front_u8, 3, &host[0], d.height, d.width, d.in_channels, net->owned, 0, allow8))) return r;
+                for (int l = 1; l < 5; ++l)
+                    if ((r = fused_block_build(net->fb_enc[l], 1, &host[1 + 2 * l], d.height >> l, d.width >> l, 0, net->owned, 0, allow8))) return r;
+                for (int l = 0; l < 4; ++l)
+                    if ((r = fused_block_build(net->fb_dec[l], 2, &host[11 + 3 * (3 - l)], d.height >> l, d.width >> l, 0, net->owned, 0, allow8))) return r;
+                return IMK_OK;
+            };
+            // Networks with int(16 * alpha) <= 8 (the reference's alpha = 0.5 ISIC models): maps of <= 8 channels live as ONE
+            // 16-byte plane per pixel in HBM and in the operand buffers (BtStage::kin8 / n8).  Every producer and consumer
+            // of such a map must be a fused block, so the mode needs all nine blocks (and their pooled outputs); otherwise
+            // everything is built with the 16-channel padding the layer-wise engines share.
+            bool want8 = f[0] <= 8 && net->w_out8;
+            if (const char *v = getenv("IMK_BT_NO_C8"); v && v[0] == '1') want8 = false;
+            if ((rc = build_all(want8))) return fail(rc);
+            if (want8) {
+                // enc[l] reads widths[l-1] channels and writes widths[l] (+ pooled); dec[l] reads widths[l], writes widths[max(l-1, 0)]
+                bool all = net->fb_enc[0].ok && fused_block_can_pool(net->fb_enc[0]);
+                for (int l = 1; l < 5; ++l)
+                    if (f[l - 1] <= 8) all = all && net->fb_enc[l].ok && (l == 4 || f[l] > 8 || fused_block_can_pool(net->fb_enc[l]));
+                for (int l = 0; l < 4; ++l)
+                    if (f[l > 0 ? l - 1 : 0] <= 8) all = all && net->fb_dec[l].ok;
+                if (net->fb_front_u8.ok) all = all && fused_block_can_pool(net->fb_front_u8);
+                if (all) net->c8 = true;
+                else if ((rc = build_all(false))) return fail(rc);
+            }
             // Head-in-epilogue variant of the level-0 decoder (K <= 3): opt-in.  Measured (r2m, B200, 512 images): the block
             // kernel is bound by the instruction issue of its epilogue warps, so the K * C0 FMAs + activation per pixel cost
             // more there (HeLa 1107 -> 1950 us, ISIC 1150 -> 1750 us per model) than the separate ensemble_im kernel they
             // replace (417 / 264 us per model); an MMA head stage (S4 + a fourth epilogue pass, r2c-r2h) measured the same.
-            if (const char *v = getenv("IMK_BT_HEAD"); v && v[0] == '1')
+            if (const char *v = getenv("IMK_BT_HEAD"); v && v[0] == '1' && !net->c8)
                 if ((rc = fused_block_build(net->fb_head, 4, &host[20], d.height, d.width, 0, net->owned, d.act_out))) return fail(rc);
         }
     }
@@ -1213,12 +1243,12 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
     const int K = d.num_outputmasks;
     if (!multiclass) IMK_REQUIRE(K == 1 || K == 3, "%s: binary IM needs K = 1 (ISIC) or 3 (HeLa), model has %d", who, K);
     IMK_REQUIRE(!lists_equal || K <= 64, "%s: lists_equal needs K <= 64", who);
-    const int c1p = nets[0]->conv.back().cin_p;
+    const int c1p = unet_c9_channels(nets[0]);
     // head path: every model's level-0 decoder kernel also runs the output layer and leaves one decision byte per pixel
     bool use_head = true;
     for (int m = 0; m < M; ++m) use_head = use_head && unet_has_head(nets[m]);
     for (int m = 0; m < M && !use_head; ++m)
-        IMK_REQUIRE(nets[m]->conv.back().cin_p == c1p, "%s: models with different int(16*alpha) padding cannot share the fused epilogue", who);
+        IMK_REQUIRE(unet_c9_channels(nets[m]) == c1p, "%s: models with different int(16*alpha) padding (or engines) cannot share the fused epilogue", who);
     if (N == 0) return IMK_OK;
     const int64_t HW = (int64_t)d.height * d.width;
     IMK_CUDA(cudaMemsetAsync(im_size, 0, sizeof(int64_t) * N, stream));
@@ -1259,7 +1289,7 @@ static int ensemble_run(imk_unet_t *const *nets, int M, bool multiclass, const u
             const HeadOut ho{multiclass ? 2 : 1, thr, dstar, strict, nullptr, nets[m]->dec};
             if ((rc = unet_trunk(nets[m], images_dev + n0 * HW * d.in_channels, IMK_IN_U8, swap_rb ? 1 : 0, n, sm, use_head ? &ho : nullptr))) return rc;
             ens.c9[m] = nets[m]->lvl[0].a;
-            ens.w[m] = nets[m]->conv.back().w_f32;
+            ens.w[m] = unet_out_weights(nets[m]);
             ens.b[m] = nets[m]->conv.back().bias;
             decs.d[m] = nets[m]->dec;
         }

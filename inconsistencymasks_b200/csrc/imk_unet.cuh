@@ -38,6 +38,8 @@ struct imk_unet {
     imk::FusedBlock fb_dec[4];                  // decoder block that OUTPUTS level l
     imk::FusedBlock fb_front_u8;                // FRONT for uint8 images: input block on the loader warps, chain of two (kind 3)
     imk::FusedBlock fb_head;                    // level-0 decoder + output layer + activation / decision (kind 4, K <= 3 on <= 32 channels)
+    bool c8 = false;                            // fused engine: maps of <= 8 channels are one 16-byte plane per pixel (c1, p1, c8, c9 at alpha = 0.5)
+    float *w_out8 = nullptr;                    // output layer [K][8] fp32 for that layout (int(16a) <= 8 only)
     std::vector<void *> owned;                  // device allocations freed at destroy
     // workspace (grown on demand), for `cap_n` images
     int64_t cap_n = 0;
@@ -60,6 +62,9 @@ namespace imk {
 // instead of c9.
 int unet_trunk(imk_unet *net, const void *images, int in_dtype, int swap_rb, int64_t n, cudaStream_t stream, const HeadOut *head = nullptr);
 inline bool unet_has_head(const imk_unet *net) { return net->engine == 2 && net->fb_head.ok; }
+// channels per pixel of c9 as the trunk leaves it (lvl[0].a) and the output layer's weights [K][that many] fp32
+inline int unet_c9_channels(const imk_unet *net) { return (net->engine == 2 && net->c8) ? 8 : net->conv.back().cin_p; }
+inline const float *unet_out_weights(const imk_unet *net) { return (net->engine == 2 && net->c8) ? net->w_out8 : net->conv.back().w_f32; }
 // Call after the last kernel that reads the model's workspace has been enqueued on `stream`.
 int unet_mark_used(imk_unet *net, cudaStream_t stream);
 int unet_reserve(imk_unet *net, int64_t n);

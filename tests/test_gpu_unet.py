@@ -41,7 +41,9 @@ def same(a, b):
 
 CASES = [
     # h, w, c, K, alpha, act           (reference configs at reduced resolution + odd widths)
-    (32, 32, 3, 1, 0.5, "sigmoid"),     # ISIC, alpha 0.5: widths 8..128 (padded to 16)
+    (32, 32, 3, 1, 0.5, "sigmoid"),     # ISIC, alpha 0.5: widths 8..128 (fused engine: 8-channel maps as one plane, taps paired)
+    (64, 48, 3, 1, 0.25, "sigmoid"),    # widths 4, 8, 16, ..: 8-channel planes on two levels, a 4-channel map inside one plane
+    (64, 96, 1, 3, 0.5, "sigmoid"),     # grayscale + 8 channels: the input-block table feeds a single plane
     (64, 48, 1, 3, 1.0, "sigmoid"),     # HeLa
     (32, 64, 3, 9, 2.0, "softmax"),     # SUIM noisy-student size: widths 32..512
     (48, 96, 3, 35, 1.0, "softmax"),    # Cityscapes aspect, K = 35
@@ -270,6 +272,7 @@ def test_head_in_epilogue_variant(U, F, monkeypatch, kind, c, K, alpha, act, h, 
     tolerance of the oracle, fused == predict -> reference IM arithmetic bit for bit; several tiles per CTA at 256x256."""
     from inconsistencymasks_b200 import _lib
     monkeypatch.setenv("IMK_BT_HEAD", "1")
+    monkeypatch.setenv("IMK_BT_NO_C8", "1")       # the head variant exists for the 16-channel layout only
     rng = np.random.default_rng(K * 7 + h)
     images = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
     weights = [U.init_weights(c, K, alpha, seed=800 + j) for j in range(2)]
