@@ -18,11 +18,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libimk.so")
+LIB = os.environ.get("IMK_LIB_OUT") or os.path.join(HERE, "libimk.so")      # IMK_LIB_OUT + IMK_BUILD_FLAGS: instrumented variants
 SOURCES = ["imk_api.cu", "imk_im.cu", "imk_morph.cu", "imk_unet.cu", "imk_conv_tc.cu", "imk_block_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("IMK_BUILD_FLAGS", "").split()
+# objects of a variant build (extra flags) live in their own directory, so switching back does not recompile everything
+OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + hashlib.sha256(os.environ["IMK_BUILD_FLAGS"].encode()).hexdigest()[:8]
+                                            if os.environ.get("IMK_BUILD_FLAGS") else ""))
 
 
 def _nvcc() -> str:
@@ -57,8 +59,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
 
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "imk.h"))
+
     def compile_one(src):
+        # per-object stamp (source + every header + flags): an edit of one .cu recompiles that file only
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        want = _digest([os.path.join(CSRC, src)] + headers)
+        ostamp = obj + ".stamp"
+        if not force and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read().strip() == want:
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -67,6 +77,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)
+        with open(ostamp, "w") as f:
+            f.write(want)
         return obj
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:

@@ -264,6 +264,7 @@ template <int KFIX, int C1FIX>
 struct HeadMma {
     static constexpr int NT = (KFIX + 7) / 8;                    // n tiles of 8 classes
     static constexpr int KS = C1FIX / 16;                        // k steps of 16 channels
+    static constexpr int XV = C1FIX / 8;                         // 16-byte vectors per pixel
     static constexpr int APITCH = C1FIX * 2 + 16;                // bytes per pixel row of the A tile: 16-byte aligned, ldmatrix conflict-free
     static constexpr int CP = NT * 8 + 1;                        // floats per pixel row of the C tile (odd: conflict-free row reads)
     static constexpr int WARP_BYTES = (32 * APITCH + 32 * CP * 4 + 15) / 16 * 16;
@@ -327,6 +328,29 @@ struct HeadMma {
 #pragma unroll
         for (int k = 0; k < KFIX; ++k) p[k] = __fadd_rn(Ct[lane * CP + k], bias[k]);
         __syncwarp();                                            // the tiles are reused by the next model / pixel batch
+    }
+};
+
+// c9 as ONE 8-channel plane (imk_unet::c8, the alpha = 0.5 networks): 8 K FMAs per pixel are cheaper than staging an MMA
+// tile.  Same interface; the fp32 weights [K][8] sit right before the bias in shared memory (both kernels lay them out so).
+template <int KFIX>
+struct HeadMma<KFIX, 8> {
+    static constexpr int NT = 0, KS = 0, XV = 1, WARP_BYTES = 0, BFRAG_WORDS = 0;
+    static __device__ __forceinline__ void prepare(const float *__restrict__, uint32_t *__restrict__) {}
+    static __device__ __forceinline__ void logits(const uint4 (&xv)[1], uint8_t *__restrict__, const uint32_t *__restrict__,
+                                                  const float *__restrict__ bias, float (&p)[KFIX]) {
+        const float *w = bias - KFIX * 8;
+        const __half2 *hv = reinterpret_cast<const __half2 *>(&xv[0]);
+        float xf[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(hv[q]); xf[2 * q] = f.x; xf[2 * q + 1] = f.y; }
+#pragma unroll
+        for (int k = 0; k < KFIX; ++k) {
+            float acc = bias[k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = __fmaf_rn(xf[j], w[k * 8 + j], acc);
+            p[k] = acc;
+        }
     }
 };
 
@@ -445,9 +469,9 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
             bool fast_arg = false;                              // arg already holds the argmax of the probabilities
             float p[KMAX];
             if constexpr (KFIX > 0) {                           // every lane takes part in the MMAs (dead lanes feed zeros)
-                uint4 xv[H::KS * 2];
+                uint4 xv[H::XV];
 #pragma unroll
-                for (int i = 0; i < H::KS * 2; ++i)
+                for (int i = 0; i < H::XV; ++i)
                     xv[i] = live ? *reinterpret_cast<const uint4 *>(ens.c9[m] + px * c1p + 8 * i) : make_uint4(0, 0, 0, 0);
                 H::logits(xv, wsm, bfrag + (size_t)m * H::BFRAG_WORDS, w_all + m * per_model + K * c1p, p);
                 if (live) {
@@ -904,7 +928,7 @@ template <typename F>
 static int dispatch_head(int K, int c1p, F &&f) {
     using std::integral_constant;
 #define IMK_HEAD(KK, CC) if (K == KK && c1p == CC) return f(integral_constant<int, KK>{}, integral_constant<int, KK>{}, integral_constant<int, CC>{})
-    IMK_HEAD(1, 16); IMK_HEAD(1, 32); IMK_HEAD(3, 16); IMK_HEAD(3, 32); IMK_HEAD(9, 16); IMK_HEAD(9, 32); IMK_HEAD(35, 16); IMK_HEAD(35, 32);
+    IMK_HEAD(1, 8); IMK_HEAD(3, 8); IMK_HEAD(1, 16); IMK_HEAD(1, 32); IMK_HEAD(3, 16); IMK_HEAD(3, 32); IMK_HEAD(9, 16); IMK_HEAD(9, 32); IMK_HEAD(35, 16); IMK_HEAD(35, 32);
 #undef IMK_HEAD
     if (K <= 4) return f(integral_constant<int, 4>{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
     if (K <= 16) return f(integral_constant<int, 16>{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});

@@ -5,7 +5,8 @@ rep = sys.argv[1]; idx = int(sys.argv[2]) if len(sys.argv) > 2 else 0; top = int
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(idx), "--launch-count", "1"], capture_output=True, text=True).stdout
 lines = out.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Kernel Name"')), len(lines))   # first (SASS) section only
+rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:end]))))
 tot = sum(int(r["# Samples"] or 0) for r in rows)
 print("total samples", tot, "instructions", len(rows))
 stall_cols = [c for c in rows[0].keys() if c.startswith("stall_") and "Not Issued" not in c]
