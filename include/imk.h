@@ -222,6 +222,42 @@ int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8
                                      uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_host,
                                      int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk);
 
+/* ------------------------------------------------------------------------- *
+ *  Adjacent components, on data that is already in HBM.
+ * ------------------------------------------------------------------------- */
+
+/* 8f-2: integer confusion counts behind benchmark_ISIC2018 / _hela / _multiclass (functions.py:1078-1339); the
+ * host forms get_IoU_binary (functions.py:1767), dice_score_numpy_binary (:1837), get_IoU_multi_unique (:1790) and
+ * pixel_accuracy (:1819) from them with the reference's own expressions.
+ * pred / gt: uint8 [N][hw] planes.  counts int64 [N][5] = |gt!=0 & pred!=0|, |gt!=0 | pred!=0|, |gt>=128 & pred>=128|,
+ * |gt>=128|, |pred>=128|.  hist int64 [N][3][256] = per value v: |gt==v|, |pred==v|, |gt==v & pred==v|. */
+int imk_seg_counts_binary(const uint8_t *pred_dev, const uint8_t *gt_dev, int64_t N, int64_t hw, int64_t *counts_dev, void *stream);
+int imk_seg_counts_multiclass(const uint8_t *pred_dev, const uint8_t *gt_dev, int64_t N, int64_t hw, int64_t *hist_dev, void *stream);
+
+/* Opt-in compact result layout for 0/255 planes (labels of the binary / HeLa paths, the IM): 8 pixels per byte,
+ * pixel i of each group of 8 in bit i.  n_bytes (multiple of 8) input bytes -> n_bytes / 8 output bytes.
+ * np.unpackbits(bits, bitorder="little") * 255 restores the planes exactly. */
+int imk_pack_bits(const uint8_t *planes_dev, int64_t n_bytes, uint8_t *bits_dev, void *stream);
+
+/* 8f-1: augment_image_and_mask(s) of the IM+ / IM++ scripts (functions.py:2725-2828, primitives :1463-1506) for a batch.
+ * The host chooses the operations (the reference's unseeded random / np.random draws); the device computes the pixels:
+ * flips + rotation on image and masks, convertScaleAbs, GaussianBlur 3/5/7 (sigma 0) and uniform noise on the image.
+ * Everything but the noise is bit-exact against OpenCV for the same parameters. */
+typedef struct imk_aug_params {
+    int flip_v, flip_h;             /* cv2.flip(x, 0) / cv2.flip(x, 1), applied in that order */
+    int rot;                        /* 0 none, 1 cv2.ROTATE_90_CLOCKWISE, 2 ROTATE_180, 3 ROTATE_90_COUNTERCLOCKWISE (1, 3: H == W) */
+    int scale_on;                   /* cv2.convertScaleAbs(image, alpha, beta) */
+    float alpha, beta;
+    int blur_k;                     /* 0, 3, 5, 7: cv2.GaussianBlur(image, (k, k), 0) */
+    int noise_max;                  /* > 0: image + randint(-noise_max, noise_max), clipped to 0..255 */
+    uint64_t seed;                  /* of the noise generator (counter-based: same seed -> same pixels) */
+} imk_aug_params;
+/* img uint8 [N,H,W,c] (or NULL: masks only), masks uint8 [mask_planes][N,H,W] (mask_planes may be 0).
+ * scratch_dev: N*H*W*c bytes, needed when any image has blur_k or noise_max > 0.  params_host: N entries. */
+int imk_augment_u8(const uint8_t *img_dev, const uint8_t *masks_dev, int64_t N, int H, int W, int c, int mask_planes,
+                   const imk_aug_params *params_host, uint8_t *img_out_dev, uint8_t *masks_out_dev,
+                   uint8_t *scratch_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,12 @@ class ProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("tag", C.c_int), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
+class AugParams(C.Structure):
+    """imk_aug_params (include/imk.h): the host-chosen operations of one augmented image."""
+    _fields_ = [("flip_v", C.c_int), ("flip_h", C.c_int), ("rot", C.c_int), ("scale_on", C.c_int),
+                ("alpha", C.c_float), ("beta", C.c_float), ("blur_k", C.c_int), ("noise_max", C.c_int), ("seed", C.c_uint64)]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); mirrors include/imk.h one to one
@@ -57,6 +63,10 @@ SIGNATURES = {
     "imk_ensemble_im_multiclass": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "imk_pseudo_label_binary_host": (_i, [_vp, _i, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
     "imk_pseudo_label_multiclass_host": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "imk_seg_counts_binary": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "imk_seg_counts_multiclass": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "imk_pack_bits": (_i, [_vp, _i64, _vp, _vp]),
+    "imk_augment_u8": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, C.POINTER(AugParams), _vp, _vp, _vp, _vp]),
 }
 
 

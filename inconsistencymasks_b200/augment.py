@@ -1,0 +1,91 @@
+"""IM+ / IM++ augmentation step: ``augment_image_and_mask(s)`` of the reference's ``functions.py``.
+
+    augment_image_and_masks   functions.py:2725-2776
+    augment_image_and_mask    functions.py:2779-2828
+    add_noise / add_noise_and_blur / apply_random_flip_and_rotation primitives   functions.py:1463-1506
+
+Same names, argument order, defaults and return types.  RNG contract: the reference draws its decisions from the
+(unseeded) ``random`` and ``np.random`` modules; ``draw_params`` makes exactly the same calls in the same order, so a
+caller that seeds both modules gets the reference's flips, rotation, brightness and blur choice.  The per-pixel noise
+(``np.random.randint(size=image.shape)`` in the reference) is replaced by ONE ``np.random.randint`` seed for the
+device's counter-based generator: uniform integers in [-max_noise, max_noise) -- distributional parity only.
+The pixels are computed by ``imk_augment_u8`` (csrc/imk_augment.cu): bit-exact against cv2 for everything but the noise.
+
+``augment_batch`` is the device-resident form the pipeline uses: it takes the blanked images and labels of a pseudo-label
+batch as CUDA tensors straight from the IM kernels and returns CUDA tensors -- no PNG round trip in between.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+
+import numpy as np
+
+from ._lib import lib, check, AugParams
+
+__all__ = ["augment_image_and_mask", "augment_image_and_masks", "draw_params", "augment_batch"]
+
+
+def draw_params(brightness_range_alpha=(0.5, 1.5), brightness_range_beta=(-25, 25), max_blur=3, max_noise=25, free_rotation=True):
+    """The decisions of functions.py:2795-2826 + 1496-1505, drawn with the reference's calls in the reference's order."""
+    p = AugParams()
+    if free_rotation:
+        p.flip_v = int(random.randint(0, 1) == 1)
+    p.flip_h = int(random.randint(0, 1) == 1)
+    if free_rotation:
+        p.rot = random.randint(0, 3)
+    p.alpha = np.random.uniform(brightness_range_alpha[0], brightness_range_alpha[1])
+    p.beta = np.random.uniform(brightness_range_beta[0], brightness_range_beta[1])
+    p.scale_on = int(random.randint(0, 1) == 1)
+    p.blur_k = {0: 0, 1: 3, 2: 5, 3: 7}.get(random.randint(0, max_blur), 0)
+    p.noise_max = int(max_noise) if max_noise > 0 else 0
+    p.seed = int(np.random.randint(0, 2 ** 31 - 1)) if max_noise > 0 else 0
+    return p
+
+
+def augment_batch(images, masks, params):
+    """images: CUDA uint8 [N,H,W,c] (or None); masks: CUDA uint8 [P,N,H,W] (or None); params: list of N AugParams.
+    Returns ``(images_out, masks_out)`` as CUDA tensors (rotations by 90 degrees need H == W)."""
+    from . import functions as F
+    torch = F._torch()
+    ref = images if images is not None else masks[0]
+    n = ref.shape[0]
+    h, w = ref.shape[1], ref.shape[2]
+    c = images.shape[3] if images is not None else 1
+    planes = masks.shape[0] if masks is not None else 0
+    arr = (AugParams * n)(*params)
+    img_out = torch.empty_like(images) if images is not None else None
+    masks_out = torch.empty_like(masks) if masks is not None else None
+    scratch = torch.empty_like(images) if images is not None and any(p.blur_k or p.noise_max for p in params) else None
+    check(lib.imk_augment_u8(images.data_ptr() if images is not None else None, masks.data_ptr() if masks is not None else None,
+                             n, h, w, c, planes, arr, img_out.data_ptr() if img_out is not None else None,
+                             masks_out.data_ptr() if masks_out is not None else None,
+                             scratch.data_ptr() if scratch is not None else None, F._stream()))
+    return img_out, masks_out
+
+
+def _one(image, masks, kw):
+    from . import functions as F
+    image = np.ascontiguousarray(np.asarray(image, dtype=np.uint8))
+    squeeze = image.ndim == 2
+    img4 = image.reshape(1, image.shape[0], image.shape[1], 1 if squeeze else image.shape[2])
+    p = draw_params(**kw)
+    d_masks = F._dev(np.stack([np.asarray(m, dtype=np.uint8) for m in masks])[:, None]) if masks else None
+    out, mo = augment_batch(F._dev(img4), d_masks, [p])
+    out = out.cpu().numpy()[0]
+    return (out[..., 0] if squeeze else out), ([m for m in mo.cpu().numpy()[:, 0]] if masks else [])
+
+
+def augment_image_and_masks(image, masks, brightness_range_alpha=(0.5, 1.5), brightness_range_beta=(-25, 25), max_blur=3, max_noise=25,
+                            free_rotation=True):
+    """functions.py:2725-2776 -> ``(image, [masks])``."""
+    return _one(image, list(masks), dict(brightness_range_alpha=brightness_range_alpha, brightness_range_beta=brightness_range_beta,
+                                         max_blur=max_blur, max_noise=max_noise, free_rotation=free_rotation))
+
+
+def augment_image_and_mask(image, mask, brightness_range_alpha=(0.5, 1.5), brightness_range_beta=(-25, 25), max_blur=3, max_noise=25,
+                           free_rotation=True):
+    """functions.py:2779-2828 -> ``(image, mask)``."""
+    out, masks = _one(image, [mask], dict(brightness_range_alpha=brightness_range_alpha, brightness_range_beta=brightness_range_beta,
+                                          max_blur=max_blur, max_noise=max_noise, free_rotation=free_rotation))
+    return out, masks[0]

@@ -48,6 +48,15 @@ __all__ = [
     "get_pos_contours", "get_min_dist", "THRESHOLD",
 ]
 
+from .evaluation import (benchmark_ISIC2018, benchmark_hela, benchmark_multiclass, get_IoU_binary, get_IoU_multi_unique,  # noqa: E402,F401
+                         pixel_accuracy, dice_score_numpy_binary, mod_pos_size, get_cell_count, convert_class_to_color_mask)
+from .augment import augment_image_and_mask, augment_image_and_masks  # noqa: E402,F401
+
+__all__ += ["benchmark_ISIC2018", "benchmark_hela", "benchmark_multiclass", "get_IoU_binary", "get_IoU_multi_unique", "pixel_accuracy",
+            "dice_score_numpy_binary", "mod_pos_size", "get_cell_count", "convert_class_to_color_mask",
+            "augment_image_and_mask", "augment_image_and_masks"]
+
+
 def _torch():
     import torch
     if not torch.cuda.is_available():

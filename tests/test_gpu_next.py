@@ -1,0 +1,284 @@
+"""GPU parity tests of the SURVEY.md 8f rows: device confusion counts / benchmark_* drivers (8f-2), the augmentation
+step (8f-1) and the bit-packed result layout, against fixtures the reference generated (oracle/make_golden_next.py),
+against cv2 itself and against the NumPy oracle."""
+import contextlib
+import io
+import os
+import random
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import ref_metrics, ref_augment
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def F():
+    from inconsistencymasks_b200 import functions
+    return functions
+
+
+@pytest.fixture(scope="module")
+def E():
+    from inconsistencymasks_b200 import evaluation
+    return evaluation
+
+
+@pytest.fixture(scope="module")
+def A():
+    from inconsistencymasks_b200 import augment
+    return augment
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (a.shape, b.shape, a.dtype, b.dtype)
+    assert np.array_equal(a, b), f"{int((a != b).sum())} of {a.size} elements differ"
+
+
+# ------------------------------------------------------------------------------------------------ 8f-2 metrics
+def test_metric_helpers_vs_reference_golden(E):
+    z = np.load(os.path.join(G, "metrics.npz"))
+    for i in range(int(z["n"])):
+        gt, pred = z[f"b{i}_gt"], z[f"b{i}_pred"]
+        iou, dice = E.get_IoU_binary(gt, pred), E.dice_score_numpy_binary(gt, pred)
+        assert iou == z[f"b{i}_iou"] and round(iou, 4) == z[f"b{i}_iou4"]
+        assert dice.dtype == z[f"b{i}_dice"].dtype and dice == z[f"b{i}_dice"]
+        gtm, predm = z[f"m{i}_gt"], z[f"m{i}_pred"]
+        assert E.get_IoU_multi_unique(predm, gtm) == z[f"m{i}_iou"]
+        assert E.pixel_accuracy(predm, gtm) == z[f"m{i}_pa"]
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 16, 16), (5, 32, 48), (64, 256, 256), (3, 208, 416)])
+def test_confusion_counts_vs_numpy(E, n, h, w):
+    rng = np.random.default_rng(n * h)
+    gt = rng.choice(np.array([0, 1, 127, 128, 255], np.uint8), size=(n, h, w))
+    pred = rng.choice(np.array([0, 255, 200, 3], np.uint8), size=(n, h, w))
+    c = E.seg_counts_binary(pred, gt)
+    for i in range(n):
+        want = [np.sum((gt[i] != 0) & (pred[i] != 0)), np.sum((gt[i] != 0) | (pred[i] != 0)), np.sum((gt[i] >= 128) & (pred[i] >= 128)),
+                np.sum(gt[i] >= 128), np.sum(pred[i] >= 128)]
+        assert list(c[i]) == [int(v) for v in want]
+    gtm = rng.integers(0, 256, size=(n, h, w), dtype=np.uint8)
+    predm = np.where(rng.random((n, h, w)) > 0.5, gtm, rng.integers(0, 256, size=(n, h, w))).astype(np.uint8)
+    hist = E.seg_counts_multiclass(predm, gtm)
+    for i in range(min(n, 4)):
+        same(hist[i, 0], np.bincount(gtm[i].ravel(), minlength=256).astype(np.int64))
+        same(hist[i, 1], np.bincount(predm[i].ravel(), minlength=256).astype(np.int64))
+        same(hist[i, 2], np.bincount(gtm[i][gtm[i] == predm[i]].ravel(), minlength=256).astype(np.int64))
+        assert E._iou_multi_unique(hist[i]) == ref_metrics.get_IoU_multi_unique(predm[i], gtm[i])
+
+
+class BatchReplay:
+    def __init__(self):
+        self.table = {}
+
+    def add(self, image, prob):
+        self.table[np.ascontiguousarray(image).astype(np.uint8).tobytes()] = prob
+
+    def predict(self, x, *a, **k):
+        x = np.asarray(x)
+        return np.stack([self.table[np.ascontiguousarray(x[i]).astype(np.uint8).tobytes()] for i in range(x.shape[0])])
+
+
+def test_benchmark_drivers_vs_reference_golden(E, tmp_path):
+    """benchmark_ISIC2018 / _multiclass / _hela on the directories the reference was run on, with the same replayed
+    probability maps: returned numbers and written prediction files are the reference's."""
+    z = np.load(os.path.join(G, "benchmarks.npz"))
+    h = w = 64
+    with contextlib.redirect_stdout(io.StringIO()):
+        # ISIC
+        idir, mdir, pdir = (str(tmp_path / "isic" / d) for d in ("images", "masks", "pred"))
+        os.makedirs(idir); os.makedirs(mdir)
+        model = BatchReplay()
+        for i, (img, gt, prob) in enumerate(zip(z["isic_images"], z["isic_gt"], z["isic_probs"])):
+            cv2.imwrite(os.path.join(idir, f"im_{i:03d}.png"), img); cv2.imwrite(os.path.join(mdir, f"im_{i:03d}.png"), gt)
+            model.add(cv2.cvtColor(img, cv2.COLOR_BGR2RGB), prob)
+        res = E.benchmark_ISIC2018(model, idir, mdir, pdir, h, w, 3, batch_size=4)
+        assert [float(v) for v in res] == list(z["isic_result"])
+        for i in range(len(z["isic_images"])):
+            same(cv2.imread(os.path.join(pdir, f"im_{i:03d}.png"), 0), z["isic_pred"][i])
+        # multiclass
+        idir, mdir, pdir = (str(tmp_path / "mc" / d) for d in ("images", "masks", "pred"))
+        os.makedirs(idir); os.makedirs(mdir)
+        model = BatchReplay()
+        for i, (img, gt, prob) in enumerate(zip(z["mc_images"], z["mc_gt"], z["mc_probs"])):
+            cv2.imwrite(os.path.join(idir, f"im_{i:03d}.png"), img); cv2.imwrite(os.path.join(mdir, f"im_{i:03d}.png"), gt)
+            model.add(cv2.cvtColor(img, cv2.COLOR_BGR2RGB), prob)
+        mapping = {tuple(int(v) for v in row[:3]): int(row[3]) for row in z["mc_mapping"]}
+        res = E.benchmark_multiclass(model, idir, mdir, pdir, h, w, 3, mapping, batch_size=4, print_results=False)
+        assert [float(v) for v in res] == list(z["mc_result"])
+        for i in range(len(z["mc_images"])):
+            same(cv2.imread(os.path.join(pdir, f"im_{i:03d}.png"), 0), z["mc_pred"][i])
+            same(cv2.imread(os.path.join(pdir, f"im_{i:03d}_color.png")), z["mc_color"][i])
+        # HeLa
+        root, pdir = str(tmp_path / "hela"), str(tmp_path / "hela_pred")
+        for d in ("brightfield", "alive", "dead", "mod_position"):
+            os.makedirs(os.path.join(root, d))
+        model = BatchReplay()
+        for i in range(len(z["hela_images"])):
+            for d, m in (("brightfield", z["hela_images"][i]), ("alive", z["hela_gt_alive"][i]), ("dead", z["hela_gt_dead"][i]),
+                         ("mod_position", z["hela_gt_pos"][i])):
+                cv2.imwrite(os.path.join(root, d, f"c_{i:03d}.png"), m)
+            model.add(z["hela_images"][i].reshape(h, w, 1), z["hela_probs"][i])
+        res = E.benchmark_hela(model, root, pdir, h, w, 1, batch_size=3)
+        assert [float(v) for v in res] == list(z["hela_result"])
+        for d in ("alive", "dead", "mod_position"):
+            for i in range(len(z["hela_images"])):
+                same(cv2.imread(os.path.join(pdir, d, f"c_{i:03d}.png"), 0), z[f"hela_pred_{d}"][i])
+
+
+def test_benchmark_with_b200_model_vs_oracle(E, tmp_path):
+    """The fused path (threshold / argmax inside the forward, counts on the device) gives the numbers the reference's
+    loop gives on the same model's own probabilities."""
+    from inconsistencymasks_b200 import unet as U
+    h = w = 64
+    rng = np.random.default_rng(9)
+    n = 37
+    with contextlib.redirect_stdout(io.StringIO()):
+        idir, mdir, pdir = (str(tmp_path / "isic" / d) for d in ("images", "masks", "pred"))
+        os.makedirs(idir); os.makedirs(mdir)
+        model = U.B200UNet(h, w, 3, 1, 0.5, "sigmoid", U.init_weights(3, 1, 0.5, seed=3))
+        imgs = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+        gts = (rng.random((n, h, w)) > 0.5).astype(np.uint8) * 255
+        for i in range(n):
+            cv2.imwrite(os.path.join(idir, f"i{i:03d}.png"), imgs[i]); cv2.imwrite(os.path.join(mdir, f"i{i:03d}.png"), gts[i])
+        miou, mdice = E.benchmark_ISIC2018(model, idir, mdir, pdir, h, w, 3, batch_size=2)
+        names = os.listdir(idir)
+        probs = model.predict(np.ascontiguousarray(np.stack([cv2.cvtColor(cv2.imread(os.path.join(idir, nm)), cv2.COLOR_BGR2RGB) for nm in names])))
+        ious, dices = [], []
+        for i, nm in enumerate(names):
+            pred = ((probs[i] > 0.5) * 255).astype(np.uint8).squeeze()
+            gt = cv2.imread(os.path.join(mdir, nm), 0)
+            same(cv2.imread(os.path.join(pdir, nm), 0), pred)
+            dices.append(round(ref_metrics.dice_score_numpy_binary(gt, pred), 4)); ious.append(round(ref_metrics.get_IoU_binary(gt, pred), 4))
+        assert miou == round(np.sum(ious) / len(ious), 3) and mdice == round(np.sum(dices) / len(dices), 3)
+        # multiclass
+        k = 9
+        idir, mdir, pdir = (str(tmp_path / "mc" / d) for d in ("images", "masks", "pred"))
+        os.makedirs(idir); os.makedirs(mdir)
+        model = U.B200UNet(h, w, 3, k, 1.0, "softmax", U.init_weights(3, k, 1.0, seed=4))
+        gtm = rng.integers(0, k, size=(n, h, w), dtype=np.uint8)
+        for i in range(n):
+            cv2.imwrite(os.path.join(idir, f"i{i:03d}.png"), imgs[i]); cv2.imwrite(os.path.join(mdir, f"i{i:03d}.png"), gtm[i])
+        mpa, miou = E.benchmark_multiclass(model, idir, mdir, pdir, h, w, 3, {(10 * j, 20, 30): j for j in range(k)}, batch_size=8, print_results=False)
+        names = os.listdir(idir)
+        probs = model.predict(np.ascontiguousarray(np.stack([cv2.cvtColor(cv2.imread(os.path.join(idir, nm)), cv2.COLOR_BGR2RGB) for nm in names])))
+        pas, ious = [], []
+        for i, nm in enumerate(names):
+            pred = np.argmax(probs[i], axis=-1)
+            gt = cv2.imread(os.path.join(mdir, nm), 0)
+            same(cv2.imread(os.path.join(pdir, nm), 0), pred.astype(np.uint8))
+            pas.append(round(ref_metrics.pixel_accuracy(pred, gt), 4)); ious.append(round(ref_metrics.get_IoU_multi_unique(pred, gt), 4))
+        assert mpa == round(np.sum(pas) / len(pas), 3) and miou == round(np.sum(ious) / len(ious), 3)
+
+
+# ------------------------------------------------------------------------------------------------ 8f-1 augmentation
+def test_augment_vs_reference_golden(A):
+    """Seeded runs of the reference's augment_image_and_mask(s) (max_noise = 0): same module seeds -> same pixels."""
+    z = np.load(os.path.join(G, "augment.npz"))
+    for seed, square, multi in (tuple(int(v) for v in row) for row in z["cases"]):
+        image, mask, mask2 = z[f"a{seed}_image"], z[f"a{seed}_mask"], z[f"a{seed}_mask2"]
+        random.seed(1000 + seed); np.random.seed(2000 + seed)
+        if multi:
+            out, masks = A.augment_image_and_masks(image.copy(), [mask.copy(), mask2.copy()], max_noise=0, free_rotation=bool(square))
+            same(masks[1], z[f"a{seed}_mask_out2"]); mask_out = masks[0]
+        else:
+            out, mask_out = A.augment_image_and_mask(image.copy(), mask.copy(), max_noise=0, free_rotation=bool(square))
+        same(out, z[f"a{seed}_out"]); same(mask_out, z[f"a{seed}_mask_out"])
+
+
+@pytest.mark.parametrize("h,w,c", [(64, 64, 3), (256, 256, 3), (48, 48, 1), (208, 416, 3), (33, 70, 3)])
+def test_augment_batch_vs_cv2(F, A, h, w, c):
+    """Every operation and combination against the cv2 calls of the reference, a batch at a time on the device."""
+    from inconsistencymasks_b200._lib import AugParams
+    rng = np.random.default_rng(h + c)
+    n = 40
+    imgs = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    masks = rng.integers(0, 35, size=(2, n, h, w), dtype=np.uint8)
+    params, dicts = [], []
+    for i in range(n):
+        d = dict(flip_v=int(rng.integers(0, 2)), flip_h=int(rng.integers(0, 2)), rot=int(rng.integers(0, 4)) if h == w else int(rng.choice([0, 2])),
+                 scale_on=int(rng.integers(0, 2)), alpha=float(rng.uniform(0.5, 1.5)), beta=float(rng.uniform(-25, 25)),
+                 blur_k=int(rng.choice([0, 3, 5, 7])))
+        p = AugParams(); p.flip_v, p.flip_h, p.rot, p.scale_on, p.alpha, p.beta, p.blur_k = (d[k] for k in ("flip_v", "flip_h", "rot", "scale_on", "alpha", "beta", "blur_k"))
+        params.append(p); dicts.append(d)
+    out, mo = A.augment_batch(F._dev(imgs), F._dev(masks), params)
+    out, mo = out.cpu().numpy(), mo.cpu().numpy()
+    for i in range(n):
+        img = imgs[i] if c == 3 else imgs[i, ..., 0]
+        want, wm = ref_augment.apply(img, [masks[0, i], masks[1, i]], dicts[i])
+        got = out[i] if c == 3 else out[i, ..., 0]
+        same(got.reshape(want.shape), want)
+        same(mo[0, i].reshape(wm[0].shape), wm[0]); same(mo[1, i].reshape(wm[1].shape), wm[1])
+
+
+def test_augment_noise_contract(F, A):
+    """Noise: uniform integers in [-max_noise, max_noise) added and clipped; same seed -> same pixels, another seed ->
+    other pixels; the mask never sees it."""
+    from inconsistencymasks_b200._lib import AugParams
+    h = w = 128
+    img = np.full((3, h, w, 3), 128, np.uint8)
+    ps = []
+    for seed in (7, 7, 8):
+        p = AugParams(); p.noise_max = 25; p.seed = seed
+        ps.append(p)
+    out, _ = A.augment_batch(F._dev(img), None, ps)
+    out = out.cpu().numpy().astype(np.int32) - 128
+    assert np.array_equal(out[0], out[1]) and not np.array_equal(out[0], out[2])
+    assert out.min() == -25 and out.max() == 24
+    counts = np.bincount((out[0] + 25).ravel(), minlength=50)
+    assert counts.min() > 0.8 * out[0].size / 50 and counts.max() < 1.2 * out[0].size / 50      # flat histogram
+    assert abs(float(np.corrcoef(out[0, :, :-1].ravel(), out[0, :, 1:].ravel())[0, 1])) < 0.02   # no neighbour correlation
+    lo = np.full((1, h, w, 3), 3, np.uint8); hi = np.full((1, h, w, 3), 250, np.uint8)
+    assert A.augment_batch(F._dev(lo), None, ps[:1])[0].cpu().numpy().min() == 0
+    assert A.augment_batch(F._dev(hi), None, ps[:1])[0].cpu().numpy().max() == 255
+    with pytest.raises(Exception):
+        q = AugParams(); q.rot = 1
+        A.augment_batch(F._dev(np.zeros((1, 32, 64, 3), np.uint8)), None, [q])
+
+
+def test_augment_consumes_pseudo_label_batch_on_device(F, A):
+    """8f-1's point: the blanked image and label of the IM kernels go straight into the augmentation, no host hop."""
+    import ctypes as C
+    import torch
+    from inconsistencymasks_b200 import unet as U
+    from inconsistencymasks_b200._lib import lib, check, AugParams
+    h = w = 64; n = 6
+    rng = np.random.default_rng(1)
+    models = [U.B200UNet(h, w, 3, 1, 0.5, "sigmoid", U.init_weights(3, 1, 0.5, seed=20 + j)) for j in range(2)]
+    imgs = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    d_img = F._dev(imgs)
+    d_out = torch.empty_like(d_img); d_lab = torch.empty((1, n, h, w), dtype=torch.uint8, device="cuda")
+    d_im = torch.empty((n, h, w), dtype=torch.uint8, device="cuda"); d_sz = torch.empty(n, dtype=torch.int64, device="cuda")
+    d_pred = torch.empty((1, n), dtype=torch.int64, device="cuda")
+    check(lib.imk_ensemble_im_binary(F._handles(models), 2, d_img.data_ptr(), n, 1, 0.5, 1, 1, 1, d_out.data_ptr(), d_lab.data_ptr(),
+                                     d_im.data_ptr(), d_sz.data_ptr(), d_pred.data_ptr(), F._stream()))
+    ps, ds = [], []
+    for i in range(n):
+        d = dict(flip_v=i & 1, flip_h=(i >> 1) & 1, rot=i % 4, scale_on=1, alpha=1.2, beta=-7.0, blur_k=[0, 3, 5, 7][i % 4])
+        p = AugParams(); p.flip_v, p.flip_h, p.rot, p.scale_on, p.alpha, p.beta, p.blur_k = d["flip_v"], d["flip_h"], d["rot"], 1, 1.2, -7.0, d["blur_k"]
+        ps.append(p); ds.append(d)
+    a_img, a_lab = A.augment_batch(d_out, d_lab, ps)
+    blanked, lab = d_out.cpu().numpy(), d_lab.cpu().numpy()
+    for i in range(n):
+        want, wm = ref_augment.apply(blanked[i], [lab[0, i]], ds[i])
+        same(a_img[i].cpu().numpy(), want); same(a_lab[0, i].cpu().numpy(), wm[0])
+
+
+# ------------------------------------------------------------------------------------------------ packed layout
+def test_pack_bits_roundtrip(F):
+    import torch
+    from inconsistencymasks_b200._lib import lib, check
+    rng = np.random.default_rng(0)
+    planes = (rng.random((3, 5, 64, 48)) > 0.5).astype(np.uint8) * 255
+    d = F._dev(planes)
+    bits = torch.empty(planes.size // 8, dtype=torch.uint8, device="cuda")
+    check(lib.imk_pack_bits(d.data_ptr(), planes.size, bits.data_ptr(), F._stream()))
+    back = np.unpackbits(bits.cpu().numpy(), bitorder="little").reshape(planes.shape) * 255
+    same(back.astype(np.uint8), planes)
+    same(bits.cpu().numpy(), np.packbits(planes.ravel() > 0, bitorder="little"))
