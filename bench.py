@@ -311,11 +311,11 @@ class HostWorkload:
     """Pinned host buffers + the host-buffer C-ABI call (imk_pseudo_label_*_host): uploads, kernels and downloads of
     consecutive chunks overlap inside the library; H2D + D2H are inside the timed region."""
 
-    def __init__(self, wl, Ne, chunk):
+    def __init__(self, wl, Ne, chunk, packed=False):
         import torch
         cfg = wl.cfg
         H, W, c = cfg["H"], cfg["W"], cfg["c"]
-        self.wl, self.Ne, self.chunk = wl, Ne, chunk
+        self.wl, self.Ne, self.chunk, self.packed = wl, Ne, chunk, packed
         self.h_img = torch.randint(0, 256, (Ne, H, W, c), dtype=torch.uint8).pin_memory()
         self.h_out = torch.empty_like(self.h_img).pin_memory()
         self.h_lab = torch.empty((wl.planes, Ne, H, W), dtype=torch.uint8).pin_memory()
@@ -323,12 +323,22 @@ class HostWorkload:
         self.h_sz = torch.empty(Ne, dtype=torch.int64).pin_memory()
         self.h_pred = torch.empty((wl.planes, Ne), dtype=torch.int64).pin_memory()
         self.h2d = Ne * H * W * c
-        self.d2h = Ne * H * W * (c + wl.planes + 1) + Ne * 8 * (1 + (0 if cfg["kind"] == "multiclass" else wl.planes))
+        stats = Ne * 8 * (1 + (0 if cfg["kind"] == "multiclass" else wl.planes))
+        self.d2h = Ne * H * W * (c + wl.planes + 1) + stats
+        if packed:       # opt-in layout: 0/255 planes as bits, no blanked image (the host holds the image it uploaded)
+            self.d2h = Ne * H * W * ((wl.planes if cfg["kind"] == "multiclass" else 0) * 8 + (0 if cfg["kind"] == "multiclass" else wl.planes) + 1) // 8 + stats
 
     def step(self):
         from inconsistencymasks_b200._lib import lib, check
         wl, cfg = self.wl, self.wl.cfg
-        if cfg["kind"] == "multiclass":
+        if self.packed and cfg["kind"] == "multiclass":
+            check(lib.imk_pseudo_label_multiclass_host_packed(wl.handles, cfg["M"], self.h_img.data_ptr(), self.Ne, 0, 1, 1, None,
+                                                              self.h_lab.data_ptr(), self.h_im.data_ptr(), self.h_sz.data_ptr(), None, self.chunk))
+        elif self.packed:
+            check(lib.imk_pseudo_label_binary_host_packed(wl.handles, cfg["M"], self.h_img.data_ptr(), self.Ne, 0, 0.5, cfg["strict"], 1, 1,
+                                                          None, self.h_lab.data_ptr(), self.h_im.data_ptr(), self.h_sz.data_ptr(),
+                                                          self.h_pred.data_ptr(), self.chunk))
+        elif cfg["kind"] == "multiclass":
             check(lib.imk_pseudo_label_multiclass_host(wl.handles, cfg["M"], self.h_img.data_ptr(), self.Ne, 0, 1, 1, self.h_out.data_ptr(),
                                                        self.h_lab.data_ptr(), self.h_im.data_ptr(), self.h_sz.data_ptr(), None, self.chunk))
         else:
@@ -360,7 +370,8 @@ def kernel_profile(wl, pk, steps=2):
         elif p["name"] in ("ensemble_im", "ensemble_votes"):
             # fused epilogue: reads M fp16 c9 maps (ensemble_im) or M decision bytes (ensemble_votes) + the image,
             # writes image, labels and IM as uint8
-            per_px = (2 * 16 * max(1, int(cfg["alpha"] + 0.99)) if p["name"] == "ensemble_im" else 1) * cfg["M"] + 2 * cfg["c"] + wl.planes + 1
+            c9_ch = 8 if int(16 * cfg["alpha"]) <= 8 else (int(16 * cfg["alpha"]) + 15) // 16 * 16     # 8-channel maps keep one 16-byte plane
+            per_px = (2 * c9_ch if p["name"] == "ensemble_im" else 1) * cfg["M"] + 2 * cfg["c"] + wl.planes + 1
             b = chunk * cfg["H"] * cfg["W"] * per_px
             row.update(gbs=b / avg_ms / 1e6, tflops=0.0, bytes=b, flops=0.0)
         rows.append(row)
@@ -533,6 +544,18 @@ def run_b200(args, name, cfg, rank, local_rank, world):
     e2e_value = world * hw.Ne * e2e_steps / e2e_s
     h2d, d2h = hw.h2d, hw.d2h
     del hw
+    # the same through the opt-in packed result layout (bit planes, blanking applied by the host to its own image)
+    hwp = HostWorkload(wl, args.e2e_images, args.e2e_chunk, packed=True)
+    for _ in range(2):
+        hwp.step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hwp.step()
+    torch.cuda.synchronize()
+    e2e_packed = dict(value=world * hwp.Ne * e2e_steps / allmax(time.perf_counter() - t0), unit="images/s", h2d_bytes_per_step=hwp.h2d,
+                      d2h_bytes_per_step=hwp.d2h, api="imk_pseudo_label_*_host_packed (bit planes; img_out = NULL)")
+    del hwp
 
     if rank != 0:
         if world > 1:
@@ -578,7 +601,7 @@ def run_b200(args, name, cfg, rank, local_rank, world):
                 e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          images_per_step=args.e2e_images, steps=e2e_steps,
                          api="imk_pseudo_label_%s_host (pinned host buffers)" % ("multiclass" if cfg["kind"] == "multiclass" else "binary")),
-                gpu_launches=int(launches), clocks=clocks, roofline=roof, roofline_step=step_roofline(cfg, value / world, pk),
+                e2e_packed=e2e_packed, gpu_launches=int(launches), clocks=clocks, roofline=roof, roofline_step=step_roofline(cfg, value / world, pk),
                 roofline_im=roof_im, cpu_baseline=cpu,
                 kernels=[{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k not in ("bytes", "flops")}
                          for r in rows[:12]],

@@ -222,6 +222,20 @@ int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, const uint8
                                      uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_host,
                                      int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk);
 
+/* Opt-in compact result layout of the two calls above (same arguments, same statistics): the 0/255 planes -- the K label
+ * planes of the binary / HeLa path and the IM -- come back as bits (imk_pack_bits: 8 pixels per byte, pixel i of a group
+ * in bit i; plane k of the labels starts at byte k*N*H*W/8), a multiclass label keeps its class-id bytes.  img_out_host
+ * may be NULL: blanking is `image[im > 0] = 0` (functions.py:2867), which a host that still holds the image it uploaded can
+ * apply itself -- then 1/8 of a byte per mask pixel crosses PCIe instead of c + planes + 1 bytes.  H*W % 8 == 0. */
+int imk_pseudo_label_binary_host_packed(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
+                                        float thr, int strict_gt, int block_in, int block_out,
+                                        uint8_t *img_out_host, uint8_t *label_bits_host, uint8_t *im_bits_host,
+                                        int64_t *im_size_host, int64_t *pred_size_host, int64_t chunk);
+int imk_pseudo_label_multiclass_host_packed(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
+                                            int block_in, int block_out,
+                                            uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_bits_host,
+                                            int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk);
+
 /* ------------------------------------------------------------------------- *
  *  Adjacent components, on data that is already in HBM.
  * ------------------------------------------------------------------------- */

@@ -63,6 +63,8 @@ SIGNATURES = {
     "imk_ensemble_im_multiclass": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "imk_pseudo_label_binary_host": (_i, [_vp, _i, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
     "imk_pseudo_label_multiclass_host": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "imk_pseudo_label_binary_host_packed": (_i, [_vp, _i, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "imk_pseudo_label_multiclass_host_packed": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64]),
     "imk_seg_counts_binary": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "imk_seg_counts_multiclass": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "imk_pack_bits": (_i, [_vp, _i64, _vp, _vp]),

@@ -131,6 +131,7 @@ struct Slot {
     uint8_t *img = nullptr, *img_out = nullptr, *labels = nullptr, *im = nullptr;
     int64_t *im_size = nullptr, *pred_size = nullptr;
     uint8_t *lists_equal = nullptr;
+    uint8_t *bits = nullptr;                // packed layout: label bit planes, then the IM bit plane
     cudaEvent_t up_done = nullptr, comp_done = nullptr, down_done = nullptr;
 };
 
@@ -143,7 +144,7 @@ struct Pipeline {
     void release() {
         for (Slot &s : slot) {
             cudaFree(s.img); cudaFree(s.img_out); cudaFree(s.labels); cudaFree(s.im);
-            cudaFree(s.im_size); cudaFree(s.pred_size); cudaFree(s.lists_equal);
+            cudaFree(s.im_size); cudaFree(s.pred_size); cudaFree(s.lists_equal); cudaFree(s.bits);
             if (s.up_done) cudaEventDestroy(s.up_done);
             if (s.comp_done) cudaEventDestroy(s.comp_done);
             if (s.down_done) cudaEventDestroy(s.down_done);
@@ -178,6 +179,7 @@ int pipeline_reserve(Pipeline &P, int64_t chunk, size_t img_bytes, size_t px_byt
         IMK_CUDA(cudaMalloc(&s.im_size, sizeof(int64_t) * chunk));
         IMK_CUDA(cudaMalloc(&s.pred_size, sizeof(int64_t) * chunk * (planes > 3 ? planes : 3)));
         IMK_CUDA(cudaMalloc(&s.lists_equal, (size_t)chunk));
+        IMK_CUDA(cudaMalloc(&s.bits, (lab_bytes + px_bytes) / 8 + 64));
         IMK_CUDA(cudaEventCreateWithFlags(&s.up_done, cudaEventDisableTiming));
         IMK_CUDA(cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming));
         IMK_CUDA(cudaEventCreateWithFlags(&s.down_done, cudaEventDisableTiming));
@@ -189,7 +191,7 @@ int pipeline_reserve(Pipeline &P, int64_t chunk, size_t img_bytes, size_t px_byt
 int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uint8_t *images, int64_t N, int swap_rb,
                       float thr, int strict, int block_in, int block_out,
                       uint8_t *img_out, uint8_t *labels, uint8_t *im, int64_t *im_size, int64_t *pred_size,
-                      uint8_t *lists_equal, int64_t chunk, const char *who) {
+                      uint8_t *lists_equal, int64_t chunk, const char *who, bool packed = false) {
     IMK_REQUIRE(nets && M >= 1 && nets[0], "%s: no models", who);
     IMK_REQUIRE(images && N >= 0, "%s: NULL images or N < 0", who);
     if (N == 0) return IMK_OK;
@@ -197,6 +199,7 @@ int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uin
     const int64_t HW = (int64_t)d.height * d.width;
     const int K = d.num_outputmasks;
     const int planes = multiclass ? 1 : K;
+    IMK_REQUIRE(!packed || HW % 8 == 0, "%s: the packed layout needs H*W to be a multiple of 8", who);
     // default: large chunks (kernel efficiency), but at least four of them in flight through the three slots
     if (chunk <= 0) chunk = std::min<int64_t>(kMaxChunk, std::max<int64_t>(64, (N + 3) / 4));
     chunk = std::min<int64_t>(chunk, N);
@@ -222,13 +225,22 @@ int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uin
             rc = imk_ensemble_im_binary(nets, M, S.img, n, swap_rb, thr, strict, block_in, block_out, img_out ? S.img_out : nullptr, S.labels,
                                         S.im, S.im_size, pred_size ? S.pred_size : nullptr, P.compute);
         if (rc) { cudaDeviceSynchronize(); return rc; }
+        // packed layout: 0/255 planes leave the device as bits (binary label planes + IM; a multiclass label keeps its ids)
+        const bool pack_lab = packed && !multiclass && labels, pack_im = packed && im;
+        const int64_t lab_bits = (int64_t)planes * n * HW / 8;
+        if (pack_lab && (rc = imk_pack_bits(S.labels, (int64_t)planes * n * HW, S.bits, P.compute))) { cudaDeviceSynchronize(); return rc; }
+        if (pack_im && (rc = imk_pack_bits(S.im, n * HW, S.bits + lab_bits, P.compute))) { cudaDeviceSynchronize(); return rc; }
         IMK_CUDA(cudaEventRecord(S.comp_done, P.compute));
         IMK_CUDA(cudaStreamWaitEvent(P.down, S.comp_done, 0));
         if (img_out) IMK_CUDA(cudaMemcpyAsync(img_out + n0 * HW * d.in_channels, S.img_out, (size_t)n * HW * d.in_channels, cudaMemcpyDeviceToHost, P.down));
-        if (labels)
+        if (labels && pack_lab)
+            for (int k = 0; k < planes; ++k)
+                IMK_CUDA(cudaMemcpyAsync(labels + ((int64_t)k * N * HW + n0 * HW) / 8, S.bits + (int64_t)k * n * HW / 8, (size_t)(n * HW / 8), cudaMemcpyDeviceToHost, P.down));
+        else if (labels)
             for (int k = 0; k < planes; ++k)     // slot planes are n*HW apart, host planes N*HW apart
                 IMK_CUDA(cudaMemcpyAsync(labels + (int64_t)k * N * HW + n0 * HW, S.labels + (int64_t)k * n * HW, (size_t)n * HW, cudaMemcpyDeviceToHost, P.down));
-        if (im) IMK_CUDA(cudaMemcpyAsync(im + n0 * HW, S.im, (size_t)n * HW, cudaMemcpyDeviceToHost, P.down));
+        if (im && pack_im) IMK_CUDA(cudaMemcpyAsync(im + n0 * HW / 8, S.bits + lab_bits, (size_t)(n * HW / 8), cudaMemcpyDeviceToHost, P.down));
+        else if (im) IMK_CUDA(cudaMemcpyAsync(im + n0 * HW, S.im, (size_t)n * HW, cudaMemcpyDeviceToHost, P.down));
         if (im_size) IMK_CUDA(cudaMemcpyAsync(im_size + n0, S.im_size, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, P.down));
         if (pred_size && !multiclass)
             for (int k = 0; k < planes; ++k)
@@ -257,4 +269,20 @@ extern "C" int imk_pseudo_label_multiclass_host(imk_unet_t *const *nets, int M, 
                                                 int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk) {
     return run_host_pipeline(nets, M, true, images_host, N, swap_rb, 0.f, 1, block_in, block_out, img_out_host, label_host, im_host,
                              im_size_host, nullptr, lists_equal_host, chunk, "imk_pseudo_label_multiclass_host");
+}
+
+extern "C" int imk_pseudo_label_binary_host_packed(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
+                                                   float thr, int strict_gt, int block_in, int block_out,
+                                                   uint8_t *img_out_host, uint8_t *label_bits_host, uint8_t *im_bits_host,
+                                                   int64_t *im_size_host, int64_t *pred_size_host, int64_t chunk) {
+    return run_host_pipeline(nets, M, false, images_host, N, swap_rb, thr, strict_gt, block_in, block_out, img_out_host, label_bits_host,
+                             im_bits_host, im_size_host, pred_size_host, nullptr, chunk, "imk_pseudo_label_binary_host_packed", true);
+}
+
+extern "C" int imk_pseudo_label_multiclass_host_packed(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
+                                                       int block_in, int block_out,
+                                                       uint8_t *img_out_host, uint8_t *label_host, uint8_t *im_bits_host,
+                                                       int64_t *im_size_host, uint8_t *lists_equal_host, int64_t chunk) {
+    return run_host_pipeline(nets, M, true, images_host, N, swap_rb, 0.f, 1, block_in, block_out, img_out_host, label_host, im_bits_host,
+                             im_size_host, nullptr, lists_equal_host, chunk, "imk_pseudo_label_multiclass_host_packed", true);
 }

@@ -282,3 +282,34 @@ def test_pack_bits_roundtrip(F):
     back = np.unpackbits(bits.cpu().numpy(), bitorder="little").reshape(planes.shape) * 255
     same(back.astype(np.uint8), planes)
     same(bits.cpu().numpy(), np.packbits(planes.ravel() > 0, bitorder="little"))
+
+
+@pytest.mark.parametrize("kind,c,K,act", [("binary", 3, 1, "sigmoid"), ("hela", 1, 3, "sigmoid"), ("multiclass", 3, 9, "softmax")])
+def test_packed_host_pipeline_equals_u8_layout(F, kind, c, K, act):
+    """imk_pseudo_label_*_host_packed: the bit planes unpack to exactly the uint8 planes of the standard call, statistics
+    identical; img_out may be NULL (the host blanks its own copy with the IM)."""
+    from inconsistencymasks_b200 import unet as U
+    from inconsistencymasks_b200._lib import lib, check
+    h, w, n = 64, 48, 21
+    rng = np.random.default_rng(K)
+    models = [U.B200UNet(h, w, c, K, 1.0, act, U.init_weights(c, K, 1.0, seed=60 + j)) for j in range(2)]
+    imgs = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    r = F._run_batch(models, imgs, kind, blank_image=imgs, block_input=True, block_output=True)
+    planes = 3 if kind == "hela" else 1
+    hs = F._handles(models)
+    im_bits = np.zeros(n * h * w // 8, np.uint8); sz = np.zeros(n, np.int64)
+    if kind == "multiclass":
+        lab = np.zeros((1, n, h, w), np.uint8)
+        check(lib.imk_pseudo_label_multiclass_host_packed(hs, 2, imgs.ctypes.data, n, 0, 1, 1, None, lab.ctypes.data, im_bits.ctypes.data,
+                                                          sz.ctypes.data, None, 8))
+        same(lab, r.labels)
+    else:
+        lab_bits = np.zeros(planes * n * h * w // 8, np.uint8); pred = np.zeros((planes, n), np.int64)
+        check(lib.imk_pseudo_label_binary_host_packed(hs, 2, imgs.ctypes.data, n, 0, 0.5, 1 if kind == "binary" else 0, 1, 1, None,
+                                                      lab_bits.ctypes.data, im_bits.ctypes.data, sz.ctypes.data, pred.ctypes.data, 8))
+        same((np.unpackbits(lab_bits, bitorder="little") * 255).astype(np.uint8).reshape(planes, n, h, w), r.labels)
+        same(pred, r.pred_size)
+    im = (np.unpackbits(im_bits, bitorder="little") * 255).astype(np.uint8).reshape(n, h, w)
+    same(im, r.im); same(sz, r.im_size)
+    blanked = imgs.copy(); blanked[im > 0] = 0                  # functions.py:2867 on the host's own copy
+    same(blanked, r.image)
