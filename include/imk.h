@@ -272,6 +272,28 @@ int imk_augment_u8(const uint8_t *img_dev, const uint8_t *masks_dev, int64_t N, 
                    const imk_aug_params *params_host, uint8_t *img_out_dev, uint8_t *masks_out_dev,
                    uint8_t *scratch_dev, void *stream);
 
+/* 8f-4: EvalNet forward of the IM++ scripts (evalnet.py:24-73; called functions.py:5733-5737, 6010-6017).
+ * n_heads 1 = get_evalnet (Dense(1)), 2 = get_evalnet_miou (Dense(b_channels) 'iou' + 'detection').
+ * b_onehot: input B is given as a uint8 class map [N,H,W] standing for its one-hot encoding over b_channels classes
+ * (functions.py:6004-6006), else as uint8 [N,H,W,b_channels].  int(16 * alpha) must be a multiple of 16.
+ * Weight order: see imk_evalnet_create in csrc/imk_evalnet.cu (layer creation order of evalnet.py). */
+typedef struct imk_evalnet imk_evalnet_t;
+typedef struct imk_evalnet_desc {
+    int height, width, a_channels, b_channels;
+    float alpha;
+    int ks;                         /* 3 */
+    int normalize_a, normalize_b;   /* x / 255 in the input block (evalnet.py:5-6) */
+    int b_onehot;
+    int n_heads;
+} imk_evalnet_desc;
+int  imk_evalnet_create(const imk_evalnet_desc *desc, const float *const *weights_host, const int64_t *weight_sizes,
+                        int n_weights, imk_evalnet_t **out);
+void imk_evalnet_destroy(imk_evalnet_t *net);
+int  imk_evalnet_param_count(const imk_evalnet_t *net, int64_t *count);
+/* out0 / out1: float32 [N][1 or b_channels]; out1 (the 'detection' head) only with n_heads == 2. */
+int  imk_evalnet_forward(imk_evalnet_t *net, const uint8_t *a_dev, const uint8_t *b_dev, int64_t N, int swap_rb_a,
+                         float *out0_dev, float *out1_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,11 @@ class ProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("tag", C.c_int), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
+class EvalNetDesc(C.Structure):
+    _fields_ = [("height", C.c_int), ("width", C.c_int), ("a_channels", C.c_int), ("b_channels", C.c_int), ("alpha", C.c_float),
+                ("ks", C.c_int), ("normalize_a", C.c_int), ("normalize_b", C.c_int), ("b_onehot", C.c_int), ("n_heads", C.c_int)]
+
+
 class AugParams(C.Structure):
     """imk_aug_params (include/imk.h): the host-chosen operations of one augmented image."""
     _fields_ = [("flip_v", C.c_int), ("flip_h", C.c_int), ("rot", C.c_int), ("scale_on", C.c_int),
@@ -68,6 +73,10 @@ SIGNATURES = {
     "imk_seg_counts_binary": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "imk_seg_counts_multiclass": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "imk_pack_bits": (_i, [_vp, _i64, _vp, _vp]),
+    "imk_evalnet_create": (_i, [C.POINTER(EvalNetDesc), _vp, _vp, _i, C.POINTER(_vp)]),
+    "imk_evalnet_destroy": (None, [_vp]),
+    "imk_evalnet_param_count": (_i, [_vp, C.POINTER(_i64)]),
+    "imk_evalnet_forward": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "imk_augment_u8": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, C.POINTER(AugParams), _vp, _vp, _vp, _vp]),
 }
 

@@ -19,7 +19,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("IMK_LIB_OUT") or os.path.join(HERE, "libimk.so")      # IMK_LIB_OUT + IMK_BUILD_FLAGS: instrumented variants
-SOURCES = ["imk_api.cu", "imk_im.cu", "imk_morph.cu", "imk_unet.cu", "imk_conv_tc.cu", "imk_block_tc.cu", "imk_augment.cu", "imk_eval.cu"]
+SOURCES = ["imk_api.cu", "imk_im.cu", "imk_morph.cu", "imk_unet.cu", "imk_conv_tc.cu", "imk_block_tc.cu", "imk_augment.cu", "imk_eval.cu", "imk_evalnet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("IMK_BUILD_FLAGS", "").split()
 # objects of a variant build (extra flags) live in their own directory, so switching back does not recompile everything

@@ -30,7 +30,7 @@ template <typename TIn>
 __global__ void __launch_bounds__(256)
 in_conv_kernel(const TIn *__restrict__ img, int c, int swap_rb, const float *__restrict__ w /*[c][cout]*/, int cout,
                const float *__restrict__ bias, const float *__restrict__ bn_scale, const float *__restrict__ bn_shift,
-               __half *__restrict__ out, int cout_p, int64_t total_px) {
+               __half *__restrict__ out, int cout_p, int64_t total_px, int normalize = 1) {
     const int chunks = cout_p / 8;
     const int64_t total = total_px * chunks;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -40,7 +40,7 @@ in_conv_kernel(const TIn *__restrict__ img, int c, int swap_rb, const float *__r
         float x[4];
         for (int ch = 0; ch < c; ++ch) {
             const int src = (swap_rb && c == 3) ? 2 - ch : ch;
-            x[ch] = __fdiv_rn((float)img[px * c + src], 255.0f);
+            x[ch] = normalize ? __fdiv_rn((float)img[px * c + src], 255.0f) : (float)img[px * c + src];   // evalnet.py:5-6: normalize is optional there
         }
         __align__(16) __half o[8];
 #pragma unroll
@@ -799,8 +799,12 @@ int unet_reserve(imk_unet *net, int64_t n) {
 
 static int launch_conv(imk_unet *net, int layer, const __half *in, const __half *in_lo, __half *out,
                        int64_t n, int h, int w, cudaStream_t stream) {
-    const ConvLayer &L = net->conv[layer];
-    if (net->engine >= 1 && conv_tc_fits(L, h, w)) {
+    return conv_layer_launch(net->conv[layer], layer, net->engine, in, in_lo, out, n, h, w, stream);
+}
+
+int conv_layer_launch(const ConvLayer &L, int layer, int engine, const __half *in, const __half *in_lo, __half *out,
+                      int64_t n, int h, int w, cudaStream_t stream) {
+    if (engine >= 1 && L.w_umma && conv_tc_fits(L, h, w)) {
         IMK_PROFILE(L.ks == 3 ? "conv_tc3" : "conv_tc1", layer, stream);
         return conv_tc_launch(L, in, in_lo, out, nullptr, n, h, w, stream);
     }
@@ -951,6 +955,63 @@ static int launch_out_probs(imk_unet *net, int64_t n, float *probs, cudaStream_t
         IMK_LAUNCHED();
         return IMK_OK;
     });
+}
+
+// ---- building blocks shared with the EvalNet forward (imk_evalnet.cu) ----------------------------------------------
+int conv_layer_pack(ConvLayer &L, int ks, int cin, int cout, const float *k /*HWIO*/, const float *b, const float *const bn[4],
+                    bool first, std::vector<void *> &owned) {
+    int rc;
+    L = ConvLayer{};
+    L.ks = ks; L.cin = cin; L.cout = cout; L.cin_p = pad_ch(cin); L.cout_p = pad_ch(cout);
+    const int64_t wsz = (int64_t)ks * ks * cin * cout;
+    if (first) {
+        std::vector<float> wf(k, k + wsz);                              // [1][1][c][cout] == [c][cout]
+        if ((rc = upload(owned, wf, &L.w_f32))) return rc;
+    } else {
+        std::vector<__half> wh((size_t)ks * ks * L.cin_p * L.cout_p, __float2half(0.f));
+        for (int tap = 0; tap < ks * ks; ++tap)
+            for (int ci = 0; ci < cin; ++ci)
+                for (int co = 0; co < cout; ++co)
+                    wh[((size_t)tap * L.cin_p + ci) * L.cout_p + co] = __float2half_rn(k[((size_t)tap * cin + ci) * cout + co]);
+        if ((rc = upload(owned, wh, &L.w_direct))) return rc;
+        if (conv_tc_supported(L) && (rc = conv_tc_pack(L, k, owned))) return rc;
+    }
+    std::vector<float> bias(L.cout_p, 0.f);
+    for (int co = 0; co < cout; ++co) bias[co] = b[co];
+    if ((rc = upload(owned, bias, &L.bias))) return rc;
+    if (bn) {
+        std::vector<float> sc(L.cout_p, 0.f), sh(L.cout_p, 0.f);
+        for (int ch = 0; ch < cout; ++ch) {
+            sc[ch] = bn[0][ch] / sqrtf(bn[3][ch] + kBnEps);
+            sh[ch] = bn[1][ch] - bn[2][ch] * sc[ch];
+        }
+        if ((rc = upload(owned, sc, &L.bn_scale))) return rc;
+        if ((rc = upload(owned, sh, &L.bn_shift))) return rc;
+        L.has_bn = true;
+    }
+    return IMK_OK;
+}
+
+int in_conv_launch(const ConvLayer &L, const void *img, int in_dtype, int c, int swap_rb, int normalize, __half *out, int64_t px,
+                   cudaStream_t stream) {
+    const int grid = grid_1d(px * (L.cout_p / 8));
+    IMK_PROFILE("in_conv", 0, stream);
+    if (in_dtype == IMK_IN_U8)
+        in_conv_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)img, c, swap_rb, L.w_f32, L.cout, L.bias, L.bn_scale, L.bn_shift,
+                                                           out, L.cout_p, px, normalize);
+    else
+        in_conv_kernel<float><<<grid, 256, 0, stream>>>((const float *)img, c, swap_rb, L.w_f32, L.cout, L.bias, L.bn_scale, L.bn_shift,
+                                                         out, L.cout_p, px, normalize);
+    IMK_LAUNCHED();
+    return IMK_OK;
+}
+
+int maxpool_launch(const __half *in, __half *out, int64_t n, int h, int w, int cp, cudaStream_t stream) {
+    const int64_t items = n * (h / 2) * (w / 2) * (cp / 8);
+    IMK_PROFILE("maxpool", -1, stream);
+    maxpool_kernel<<<grid_1d(items), 256, 0, stream>>>(in, out, n, h, w, cp);
+    IMK_LAUNCHED();
+    return IMK_OK;
 }
 
 }  // namespace imk

@@ -71,6 +71,17 @@ int unet_reserve(imk_unet *net, int64_t n);
 int64_t max_chunk();                    // images per trunk pass (bounds the workspace; IMK_CHUNK overrides the default)
 #define kMaxChunk (imk::max_chunk())
 
+// Building blocks shared with the EvalNet forward (imk_evalnet.cu): one Conv2D (+ReLU)(+BN) packed for every engine and
+// launched on the engine that fits (1 / 2: layer-wise tcgen05 when a strip plan exists, else the direct kernel).
+// bn: {gamma, beta, moving_mean, moving_variance} or null.  first: the 1x1 layer that reads the image (fp32 weights).
+int conv_layer_pack(ConvLayer &L, int ks, int cin, int cout, const float *hwio, const float *bias, const float *const bn[4],
+                    bool first, std::vector<void *> &owned);
+int conv_layer_launch(const ConvLayer &L, int tag, int engine, const __half *in, const __half *in_lo, __half *out,
+                      int64_t n, int h, int w, cudaStream_t stream);
+int in_conv_launch(const ConvLayer &L, const void *img, int in_dtype, int c, int swap_rb, int normalize, __half *out, int64_t px,
+                   cudaStream_t stream);
+int maxpool_launch(const __half *in, __half *out, int64_t n, int h, int w, int cp, cudaStream_t stream);
+
 // imk_conv_tc.cu: tcgen05 implicit-GEMM engine.  Returns IMK_OK when it handled the layer.
 bool conv_tc_supported(const ConvLayer &L);
 bool conv_tc_fits(const ConvLayer &L, int h, int w);   // a strip configuration exists for this resolution

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["layer_plan", "count_params", "init_weights"]
+__all__ = ["layer_plan", "count_params", "init_weights", "evalnet_plan", "init_evalnet_weights"]
 
 
 def layer_plan(i_channels, num_outputmasks, alpha, ks=3):
@@ -64,4 +64,42 @@ def init_weights(i_channels, num_outputmasks, alpha, ks=3, seed=0, trained_like=
                         rng.normal(0, 0.1, ch).astype(np.float32), rng.uniform(0.5, 1.5, ch).astype(np.float32)]
             else:
                 out += [np.ones(ch, np.float32), np.zeros(ch, np.float32), np.zeros(ch, np.float32), np.ones(ch, np.float32)]
+    return out
+
+
+def evalnet_plan(a_channels, b_channels, alpha, n_heads=1, ks=3):
+    """Parameterised layers of get_evalnet / get_evalnet_miou in the order evalnet.py creates them (evalnet.py:24-73):
+    branch A (input block, conv_block), branch B, five trunk conv_blocks, the Dense head(s) as ``("dense", cin, cout)``."""
+    f = [int(k * alpha) for k in (16, 32, 64, 128, 256)]
+    plan = []
+    for c_in in (a_channels, b_channels):
+        plan += [("conv", 1, c_in, f[0]), ("bn", f[0]), ("conv", ks, f[0], f[0]), ("conv", 1, f[0], f[0]), ("bn", f[0])]
+    cin = 2 * f[0]
+    for w in f:
+        plan += [("conv", ks, cin, w), ("conv", 1, w, w), ("bn", w)]
+        cin = w
+    n_out = 1 if n_heads == 1 else b_channels
+    plan += [("dense", f[4], n_out)] * n_heads
+    return plan
+
+
+def init_evalnet_weights(a_channels, b_channels, alpha, n_heads=1, ks=3, seed=0):
+    """Seeded random EvalNet weights in ``evalnet_plan`` order (he_normal convs, glorot-like Dense, trained-like BN)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for item in evalnet_plan(a_channels, b_channels, alpha, n_heads, ks):
+        if item[0] == "conv":
+            _, k, cin, cout = item
+            std = np.sqrt(2.0 / (k * k * cin))
+            out.append((np.clip(rng.standard_normal((k, k, cin, cout)), -2, 2) * std).astype(np.float32))
+            out.append(rng.normal(0, 0.05, cout).astype(np.float32))
+        elif item[0] == "bn":
+            ch = item[1]
+            out += [rng.uniform(0.5, 1.5, ch).astype(np.float32), rng.normal(0, 0.1, ch).astype(np.float32),
+                    rng.normal(0, 0.1, ch).astype(np.float32), rng.uniform(0.5, 1.5, ch).astype(np.float32)]
+        else:
+            _, cin, cout = item
+            lim = np.sqrt(6.0 / (cin + cout))
+            out.append(rng.uniform(-lim, lim, (cin, cout)).astype(np.float32))
+            out.append(rng.normal(0, 0.05, cout).astype(np.float32))
     return out

@@ -313,3 +313,36 @@ def test_packed_host_pipeline_equals_u8_layout(F, kind, c, K, act):
     same(im, r.im); same(sz, r.im_size)
     blanked = imgs.copy(); blanked[im > 0] = 0                  # functions.py:2867 on the host's own copy
     same(blanked, r.image)
+
+
+# ------------------------------------------------------------------------------------------------ 8f-4 EvalNet
+@pytest.mark.parametrize("h,w,ca,cb,alpha,heads", [(64, 64, 3, 1, 1.0, 1), (128, 64, 3, 1, 2.0, 1), (64, 128, 1, 3, 2.0, 2), (64, 64, 3, 9, 1.0, 2),
+                                                   (256, 256, 3, 1, 1.0, 1), (208, 416, 3, 35, 2.0, 2)])
+def test_evalnet_forward_vs_fp32_oracle(h, w, ca, cb, alpha, heads):
+    """get_evalnet / get_evalnet_miou against the torch fp32 restatement (oracle/ref_evalnet.py): sigmoid scores within
+    5e-3 (fp16 activations, fp32 accumulation).  The one-hot input goes through the look-up layer."""
+    from oracle import ref_evalnet
+    from inconsistencymasks_b200 import evalnet as EV
+    rng = np.random.default_rng(h + cb)
+    n = 5 if h < 200 else 2
+    a = rng.integers(0, 256, size=(n, h, w, ca), dtype=np.uint8)
+    weights = EV.init_evalnet_weights(ca, cb, alpha, heads, seed=cb)
+    if heads == 1:
+        b = (rng.random((n, h, w, cb)) > 0.5).astype(np.uint8) * 255
+        model = EV.get_evalnet(h, w, ca, cb, alpha, weights=weights)
+        got = model.predict([a, b])
+        want = ref_evalnet.forward(a, b, weights, alpha, 1, True, True)
+        assert got.shape == (n, 1) and got.dtype == np.float32
+        assert float(np.abs(got - want).max()) <= 5e-3, float(np.abs(got - want).max())
+    else:
+        cls = rng.integers(0, cb, size=(n, h, w))
+        b = np.stack([(cls == k).astype(np.int32) for k in range(cb)], axis=-1)       # functions.py:6005
+        b[0, :4, :4, :] = 0                                                            # pixels outside every class
+        model = EV.get_evalnet_miou(h, w, ca, cb, alpha, weights=weights)
+        iou, det = model.predict([a, b])
+        w_iou, w_det = ref_evalnet.forward(a, b, weights, alpha, 2, True, False)
+        assert iou.shape == (n, cb) and det.shape == (n, cb)
+        assert float(np.abs(iou - w_iou).max()) <= 5e-3 and float(np.abs(det - w_det).max()) <= 5e-3
+    from inconsistencymasks_b200.weights import evalnet_plan
+    assert model.count_params() == sum((it[1] ** 2 * it[2] * it[3] + it[3]) if it[0] == "conv" else (4 * it[1] if it[0] == "bn" else it[1] * it[2] + it[2])
+                                       for it in evalnet_plan(ca, cb, alpha, heads))
