@@ -785,6 +785,11 @@ int unet_reserve(imk_unet *net, int64_t n) {
     }
     const size_t dec_off = total;
     total += ((size_t)n * net->desc.height * net->desc.width + 255) / 256 * 256;
+    // IMK_WS_LIMIT_MB: refuse workspaces above this size (deployments that share a GPU; also how the tests reach this path)
+    if (const char *v = getenv("IMK_WS_LIMIT_MB"); v && v[0] && total > (size_t)atoll(v) * (1u << 20)) {
+        set_error("unet workspace: %zu bytes for %lld images exceed IMK_WS_LIMIT_MB=%s", total, (long long)n, v);
+        return IMK_ENOMEM;
+    }
     if (cudaMalloc(&net->ws, total) != cudaSuccess) { cudaGetLastError(); set_error("unet workspace: cudaMalloc(%zu) failed", total); return IMK_ENOMEM; }
     net->dec = reinterpret_cast<uint8_t *>((char *)net->ws + dec_off);
     net->ws_bytes = total;

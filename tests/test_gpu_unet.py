@@ -355,3 +355,35 @@ def test_keras_like_surface(U, tmp_path):
     from inconsistencymasks_b200 import _lib
     with pytest.raises(_lib.ImkError):
         U.get_unet(30, 32, 3, 9, 1.0, "relu", "softmax")      # not a multiple of 16
+
+
+def test_workspace_allocation_failure_is_reported(U, monkeypatch):
+    """A workspace that cannot be allocated is IMK_ENOMEM with a message, nothing is left half-initialised, and the same
+    model still serves a batch that fits (6.2 GB per model at chunk 512 had no failure-path test)."""
+    from inconsistencymasks_b200 import _lib
+    h = w = 64
+    model = U.B200UNet(h, w, 3, 1, 1.0, "sigmoid", U.init_weights(3, 1, 1.0, seed=2))
+    x = np.random.default_rng(0).integers(0, 256, size=(64, h, w, 3), dtype=np.uint8)
+    monkeypatch.setenv("IMK_WS_LIMIT_MB", "1")
+    with pytest.raises(_lib.ImkError) as e:
+        model.predict(x)
+    assert "error -3" in str(e.value) and "workspace" in str(e.value)
+    monkeypatch.setenv("IMK_WS_LIMIT_MB", "4096")
+    p = model.predict(x[:4])
+    assert p.shape == (4, h, w, 1) and np.isfinite(p).all()
+    same(p, model.predict(x)[:4])
+
+
+def test_predict_is_stateless_after_pseudo_label_calls(U, F, tmp_path):
+    """a driver call with rgb=True (channel swap) must not change what a later .predict returns."""
+    import cv2
+    h = w = 32
+    rng = np.random.default_rng(5)
+    models = [U.B200UNet(h, w, 3, 1, 0.5, "sigmoid", U.init_weights(3, 1, 0.5, seed=40 + j)) for j in range(2)]
+    x = rng.integers(0, 256, size=(3, h, w, 3), dtype=np.uint8)
+    before = models[0].predict(x)
+    d = tmp_path / "in"; d.mkdir()
+    for i in range(3):
+        cv2.imwrite(str(d / f"a{i}.png"), x[i])
+    F.create_pseudo_labels_im_ISIC_2018(models, h, w, 3, str(d), str(tmp_path / "out"), rgb=True, erode_kernel=0, dilate_kernel=0)
+    same(models[0].predict(x), before)
