@@ -104,6 +104,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity), "r"(kBtSuspendNs) : "memory");
 }
+#ifdef IMK_BT_ACC_BUILD
+__device__ __forceinline__ uint32_t bt_clk() { uint32_t c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); return c; }
+#endif
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -138,6 +141,14 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c, int x, int y, int n, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(x), "r"(y), "r"(n), "r"(smem_u32(bar)) : "memory");
+}
+
+// 8-channel maps: a pixel is ONE 16-byte vector, so a tile row is contiguous in memory.  The map is then described as
+// uint64 [N][H][2W] and a box row is ONE contiguous run of 16 * pitch bytes instead of `pitch` 16-byte pieces at a stride
+// (the TMA unit issues one request per inner-box row: 1408 requests per plane of a 14x86 tile otherwise).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int n, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(n), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void tile_coords(const BtArgs &a, long long tile, int &n, int &y0, int &x0) {
@@ -835,6 +846,15 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         // =====================================================================================
         //  loaders
         // =====================================================================================
+#ifdef IMK_BT_ACC_BUILD
+        uint32_t ld_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long ld_acc[5] = {0, 0, 0, 0, 0};
+#define LD_T(k) ld_t[k] = bt_clk()
+#define LD_ACC() do { ld_acc[0] += ld_t[1] - ld_t[0]; ld_acc[1] += ld_t[2] - ld_t[1]; ld_acc[2] += ld_t[3] - ld_t[2]; ld_acc[3] += ld_t[4] - ld_t[3]; ld_acc[4] += ld_t[6] - ld_t[5]; ld_t[5] = ld_t[6] = 0; } while (0)
+#else
+#define LD_T(k) do { } while (0)
+#define LD_ACC() do { } while (0)
+#endif
         const int lt = tid - (kBtEpiWarps + 1) * 32;
         constexpr int NL = kBtLoadWarps * 32;
         const int Pn = kHasS1 ? a.Pn0 : a.Pn1;
@@ -847,7 +867,9 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         auto pool_tile = [&](long long j) {
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + j * gridDim.x, n, y0, x0);
+            LD_T(5);
             mbar_wait(e3_done, (uint32_t)(j & 1));
+            LD_T(6);
             const int C8 = a.out_c >> 3;                                  // 16-byte vectors per pixel
             const int pw = min(a.Tw, a.W - x0) >> 1, ph = min(a.Th, a.H - y0) >> 1;
             const int Wp = a.W >> 1;
@@ -865,7 +887,10 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 *reinterpret_cast<uint4 *>(p0 + (py * Wp + px) * a.out_c + cv * 8) = max_h8(max_h8(v0, v1), max_h8(v2, v3));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(o_free);
+            // relaxed: o_free only says that the staging tile has been READ (the loads above have returned -- their values fed
+            // the stores); a releasing arrive would first wait for the pooled global stores to be acknowledged, ~1.5k cycles
+            // on the loader warps per tile (measured with the phase timers of the ACC build)
+            if (lane == 0) mbar_arrive_relaxed(o_free);
         };
         const long long pool_lag = kHasS1 ? 3 : 2;                      // the tile whose E3 runs while this load is in flight
         for (long long i = 0; i < n_my; ++i) {
@@ -876,7 +901,9 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             const uint32_t lph = kHasS1 ? (uint32_t)(i & 1) : (uint32_t)((i >> 1) & 1);
             uint8_t *buf = kHasS1 ? A0 : A1 + (size_t)lb * a.a1_stride;
             if (first) BT_TL(2, i, 0);
+            LD_T(0);
             if (kHasS1 ? i >= 1 : i >= 2) mbar_wait(&ld_empty[lb], lph ^ 1u);
+            LD_T(1);
             if (first) BT_TL(2, i, 1);
             if constexpr (KIND == 0) {
                 // image -> x/255 split into fp16 hi + lo so that the first layer keeps ~22 bits of the input and
@@ -982,7 +1009,8 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 if (first && elect_one()) {
                     mbar_expect_tx(&tma_full[lb], (uint32_t)KC * 16u * (uint32_t)npos);
                     const uint32_t dst = smem_u32(buf);
-                    for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, &tma_full[lb]);
+                    if (a.tm_flat8) tma_load_3d(dst, &a.tm_in, 2 * (x0 - 1), y0 - 1, n, &tma_full[lb]);
+                    else for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, &tma_full[lb]);
                 }
                 __syncwarp();
                 mbar_wait(&tma_full[lb], lph);
@@ -995,7 +1023,8 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 if (first && elect_one()) {
                     mbar_expect_tx(&tma_full[0], (uint32_t)KC * 16u * (uint32_t)npos);
                     const uint32_t dst = smem_u32(buf);
-                    for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, &tma_full[0]);
+                    if (a.tm_flat8) tma_load_3d(dst, &a.tm_in, 2 * (x0 - 1), y0 - 1, n, &tma_full[0]);
+                    else for (int kc = 0; kc < KC; ++kc) tma_load_4d(dst + (uint32_t)(kc * Pn) * 16u, &a.tm_in, kc * 8, x0 - 1, y0 - 1, n, &tma_full[0]);
                 }
                 __syncwarp();
                 const __half *lo_n = a.in_lo + (long long)n * (a.H >> 1) * (a.W >> 1) * a.ld_cp;
@@ -1044,14 +1073,24 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 }
                 if (!landed) mbar_wait(&tma_full[0], (uint32_t)(i & 1));
             }
+            LD_T(2);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ld_full[lb]);
             if (first) BT_TL(2, i, 2);
+            LD_T(3);
             if (a.out_pool && i >= pool_lag) pool_tile(i - pool_lag);
+            LD_T(4);
+            LD_ACC();
         }
         if (a.out_pool)
             for (long long j = n_my > pool_lag ? n_my - pool_lag : 0; j < n_my; ++j) pool_tile(j);
+#ifdef IMK_BT_ACC_BUILD
+        if (a.dbg && blockIdx.x == 0 && first && lane == 0) {
+            for (int j = 0; j < 5; ++j) a.dbg[j] = (long long)ld_acc[j];
+            a.dbg[5] = n_my;
+        }
+#endif
     }
     // ---- teardown ----------------------------------------------------------------------------
     tc_fence_before();
@@ -1310,6 +1349,21 @@ int make_map(CUtensorMap *map, const void *base, int64_t n, int h, int w, int c,
     return IMK_OK;
 }
 
+// 8-channel fp16 NHWC map as uint64 [n][h][2w] with boxes {2 box_w, box_h, 1} (see tma_load_3d)
+static int make_map_flat8(CUtensorMap *map, const void *base, int64_t n, int h, int w, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return IMK_ECUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)w * 2, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (flat 8-channel) failed (%d) for [%lld,%d,%d] box %dx%d", (int)r, (long long)n, h, w, box_w, box_h); return IMK_ECUDA; }
+    return IMK_OK;
+}
+
 static int bt_upload(FusedBlock &fb, const std::vector<__half> &w, const std::vector<float> &par, std::vector<void *> &owned) {
     void *pw = nullptr, *pp = nullptr;
     if (cudaMalloc(&pw, w.size() * sizeof(__half)) != cudaSuccess) { set_error("fused block: cudaMalloc failed"); return IMK_ENOMEM; }
@@ -1430,7 +1484,10 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
     a.n_tiles = (long long)n * a.tiles_x * a.tiles_y;
     if (a.n_tiles <= 0) return IMK_OK;
     if (a.load_kind == 1 || a.load_kind == 2) {
-        int rc = make_map(&a.tm_in, in, n, a.H, a.W, a.ld_cp, a.pitch, a.Th + 2);
+        a.tm_flat8 = (a.ld_cp == 8 && a.pitch <= 128) ? 1 : 0;
+        if (const char *v = getenv("IMK_BT_NO_FLAT8"); v && v[0] == '1') a.tm_flat8 = 0;
+        int rc = a.tm_flat8 ? make_map_flat8(&a.tm_in, in, n, a.H, a.W, a.pitch, a.Th + 2)
+                            : make_map(&a.tm_in, in, n, a.H, a.W, a.ld_cp, a.pitch, a.Th + 2);
         if (rc) return rc;
     }
     // width classes of the block (see bt_kernel)
@@ -1461,6 +1518,17 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
     }
     kern<<<grid, fb.ctas_per_sm == 2 ? bt_threads(8, 4) : bt_threads(16, 8), fb.smem, stream>>>(a);
     IMK_LAUNCHED();
+#ifdef IMK_BT_ACC_BUILD
+    if (a.dbg) {
+        long long h[8];
+        IMK_CUDA(cudaStreamSynchronize(stream));
+        IMK_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        const double nt = (double)(h[5] > 0 ? h[5] : 1);
+        fprintf(stderr, "[imk] loader phases kind=%d %dx%d tile %dx%d, CTA 0 warp 0, %lld tiles, cycles per tile: wait ld_empty %.0f | load + transform %.0f | fence + arrive %.0f | pool (incl. wait e3 %.0f) %.0f\n",
+                a.load_kind, a.H, a.W, a.Th, a.Tw, h[5], h[0] / nt, h[1] / nt, h[2] / nt, h[4] / nt, h[3] / nt);
+        return IMK_OK;
+    }
+#endif
     if (a.dbg) {
         long long h[6 * 16 * 8];
         IMK_CUDA(cudaStreamSynchronize(stream));

@@ -45,6 +45,7 @@ struct BtArgs {
     int o_off;                          // output staging tile [Th][Tw][out_c] fp16
     int out_c;                          // channels per pixel of the output map in HBM (s3.n, or 8 when s3.n8)
     int lut_off;                        // FRONT: 256-entry table of x/255 as fp16 hi | lo << 16
+    int tm_flat8;                       // tm_in describes an 8-channel map as uint64 [N][H][2W] (contiguous tile rows)
     alignas(64) CUtensorMap tm_in;      // TMA map (ENC / DEC): {8 ch, pitch, Th + 2, 1} boxes of the fp16 NHWC input / skip map
     // Epilogue constants, read as constant-bank operands (no loads): the BN scale is folded into the weights, so a
     // stage's epilogue is  h = fp16(acc + cpar[s][c]);  h = min(max(h, clo[s][c]), chi[s][c])  on packed halves
