@@ -464,15 +464,23 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
         const bool uniform = (p0 + 256 <= (n_first + 1) * HW) && (p0 + 256 <= total_px);
         const int64_t n = live ? (uniform ? n_first : (int64_t)((uint32_t)px / (uint32_t)HW)) : -1;
         const int64_t n_u = uniform ? n_first : n;
+        uint4 x_next = make_uint4(0, 0, 0, 0);
+        if constexpr (KFIX > 0 && H::XV == 1) { if (live) x_next = ldg_stream(ens.c9[0] + px * c1p); }
         for (int m = 0; m < M; ++m) {
             int arg = 0;
             bool fast_arg = false;                              // arg already holds the argmax of the probabilities
             float p[KMAX];
             if constexpr (KFIX > 0) {                           // every lane takes part in the MMAs (dead lanes feed zeros)
                 uint4 xv[H::XV];
+                if constexpr (H::XV == 1) {
+                    // one 16-byte plane per model: the next model's vector is requested before this one is used
+                    xv[0] = x_next;
+                    x_next = (live && m + 1 < M) ? ldg_stream(ens.c9[m + 1] + px * c1p) : make_uint4(0, 0, 0, 0);
+                } else {
 #pragma unroll
-                for (int i = 0; i < H::XV; ++i)
-                    xv[i] = live ? *reinterpret_cast<const uint4 *>(ens.c9[m] + px * c1p + 8 * i) : make_uint4(0, 0, 0, 0);
+                    for (int i = 0; i < H::XV; ++i)
+                        xv[i] = live ? *reinterpret_cast<const uint4 *>(ens.c9[m] + px * c1p + 8 * i) : make_uint4(0, 0, 0, 0);
+                }
                 H::logits(xv, wsm, bfrag + (size_t)m * H::BFRAG_WORDS, w_all + m * per_model + K * c1p, p);
                 if (live) {
                     if (kMulticlass && act == IMK_ACT_SOFTMAX) {
@@ -1311,7 +1319,7 @@ static int launch_ens(const EnsPtrs &ens, int M, int c1p, int K, int act, float 
     size_t smem = (size_t)M * ((K * c1p + K + 3) / 4 * 4) * sizeof(float) + 8 * 32;            // weights + bias per model, class-id bytes per warp
     if constexpr (KFIX > 0) smem += (size_t)M * HeadMma<KFIX, C1FIX>::BFRAG_WORDS * 4 + 8 * (size_t)HeadMma<KFIX, C1FIX>::WARP_BYTES;
     IMK_CUDA(cudaFuncSetAttribute(ensemble_im_kernel<KMAX, MC, KFIX, C1FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = grid_1d(total_px, 256, 4);
+    const int grid = grid_1d(total_px, 256, (KFIX > 0 && C1FIX == 8) ? 8 : 4);    // the 8-channel head is light on registers: more CTAs in flight
     const float dstar = (!MC && KFIX > 0 && act == IMK_ACT_SIGMOID) ? sigmoid_dstar(thr, strict) : 0.f;
     IMK_PROFILE("ensemble_im", -1, stream);
     ensemble_im_kernel<KMAX, MC, KFIX, C1FIX><<<grid, 256, smem, stream>>>(ens, M, c1p, K, act, thr, strict, dstar, total_px, HW, N, plane_stride, img, c,
