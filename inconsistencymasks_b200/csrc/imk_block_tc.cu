@@ -544,7 +544,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                     const int r = (int)__umulhi((unsigned)m, a.pitch_magic), c = m - r * a.pitch;
                     const int y = y0 - 1 + r, x = x0 - 1 + c;
                     const bool inside = r < a.Th + 2 && y >= 0 && y < a.H && x >= 0 && x < a.W;
-                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.n), inside, true, A1j + (size_t)m * 16};
+                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s1.col + b * a.s1.cs), inside, true, A1j + (size_t)m * 16};
                 });
             });
             // warps without a block of their own still pace themselves on the stage (a free-running warp would
@@ -565,7 +565,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             with_nch<N2>(a.s2, [&](auto nch) {
                 epi_stage<1, decltype(nch)::value, true, kBtEpiGroups>(a, a.s2.nb, g, acc2_full, par_, (size_t)a.Pn2 * 16, 0, [&](int b) {
                     const int m = b * 128 + q * 32 + lane;
-                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.n), true, true, A2 + (size_t)m * 16};
+                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s2.col + b * a.s2.cs), true, true, A2 + (size_t)m * 16};
                 });
             });
             mbar_wait(&acc2_full[a.s2.nb - 1], par_);
@@ -605,7 +605,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                     const int m = b * 128 + q * 32 + lane;
                     const int ro = (int)__umulhi((unsigned)m, a.pitch_magic), co = m - ro * a.pitch;
                     const bool valid = ro < a.Th && co < a.Tw;
-                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.n), true, valid,
+                    return EpiBlk{tmem + lane_base + (uint32_t)(a.s3.col + b * a.s3.cs), true, valid,
                                   OT + ((size_t)(ro * a.Tw + co) * a.out_c) * 2};
                 });
             });
@@ -661,7 +661,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         const uint32_t pitch = (uint32_t)a.pitch;
         // descriptor words: lo = addr >> 4 | LBO >> 4 << 16 ; hi = SBO >> 4 | version 1 << 14
         constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
-        struct StageRegs { uint32_t a_lo, a_step, b_lo, b_unit, idesc, d, n, nb, ksteps, kin8; };
+        struct StageRegs { uint32_t a_lo, a_step, b_lo, b_unit, idesc, d, n, cs, nb, ksteps, kin8; };
         auto make_stage = [&](const BtStage &st, uint32_t abase, int Pn) {
             StageRegs r;
             r.a_lo = (abase >> 4) | (st.kin8 ? 0u : (uint32_t)Pn << 16);   // LBO = Pn * 16 bytes (kin8: set per MMA, 0 for a 1x1 stage)
@@ -671,7 +671,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             r.b_unit = (uint32_t)st.n * 2u;                           // n * 32 bytes per (tap, K step)
             r.idesc = (1u << 4) | ((uint32_t)(st.n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             r.d = tmem + (uint32_t)st.col;
-            r.n = (uint32_t)st.n; r.nb = (uint32_t)st.nb; r.ksteps = (uint32_t)st.ksteps;
+            r.n = (uint32_t)st.n; r.cs = (uint32_t)st.cs; r.nb = (uint32_t)st.nb; r.ksteps = (uint32_t)st.ksteps;
             return r;
         };
         const uint32_t cgm1 = (uint32_t)a.cgm1, cgm3 = (uint32_t)a.cgm3;
@@ -684,7 +684,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         // one M block of a 1x1 stage.  KS > 0: compile-time K steps (fully unrolled); KS == 0: runtime loop.
         auto block_1x1 = [&](auto ks_tag, const StageRegs &r, uint32_t b) {
             constexpr int KS = decltype(ks_tag)::value;
-            const uint32_t d = r.d + b * r.n;
+            const uint32_t d = r.d + b * r.cs;
             uint32_t al = r.a_lo + b * 128u, bl = r.b_lo;
             if constexpr (KS > 0) {
 #pragma unroll
@@ -696,7 +696,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
         // one M block of the 3x3 stage: 9 taps x K steps, the taps are offsets dy * pitch + dx into the flat tile
         auto block_3x3 = [&](auto ks_tag, const StageRegs &r, uint32_t b) {
             constexpr int KS = decltype(ks_tag)::value;
-            const uint32_t d = r.d + b * r.n;
+            const uint32_t d = r.d + b * r.cs;
             const uint32_t arow0 = r.a_lo + b * 128u;
             if constexpr (KS < 0) {
                 // single 8-channel plane: K = 16 of an MMA = the 8 channels of TWO taps, LBO = the distance between them
@@ -1208,6 +1208,13 @@ static bool bt_disabled() {
 static inline int round8(int v) { return (v + 7) / 8 * 8; }
 
 struct BtGeom { int nb1, nb2, Pn0, Pn1, Pn2, cols; size_t bytes; };
+// TMEM columns between the M blocks of a stage / columns of the whole stage (IMK_BT_NO_CS8=1: always n, for A/B runs)
+static inline int bt_cs(const BtStage &st) {
+    static int off = -1;
+    if (off < 0) { const char *v = getenv("IMK_BT_NO_CS8"); off = (v && v[0] == '1') ? 1 : 0; }
+    return (st.n8 && !off) ? 8 : st.n;
+}
+static inline int bt_span(const BtStage &st, int nb) { return nb == 0 ? 0 : bt_cs(st) * nb + (st.n - bt_cs(st)); }
 static inline int bt_planes(const BtStage &st) { return st.kin8 ? 1 : st.ksteps * 2; }     // 16-byte planes of the stage's A operand
 
 // shared-memory / TMEM footprint of a candidate tile; plane strides are multiples of 8 positions so that every
@@ -1220,7 +1227,11 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
     g.nb1 = a.has_s1 ? ((th + 2) * pitch + 127) / 128 : 0;
     g.nb2 = (th * pitch + 127) / 128;
     if (g.nb1 > kBtMaxBlocks || g.nb2 > kBtMaxBlocks) return false;
-    g.cols = g.nb1 * n1 + g.nb2 * n2 + g.nb2 * n3;
+    // TMEM columns: a stage with <= 8 real outputs (n8) spaces its M blocks 8 columns apart -- the UMMA still writes
+    // N = 16 columns, but the upper eight are the NEXT block's, overwritten by it before anybody reads them (the blocks of a
+    // stage are issued in order and read only after the stage's MMAs have retired) -- so twice the pixels fit a tile
+    g.cols = (a.has_s1 ? bt_span(a.s1, g.nb1) : 0) + bt_span(a.s2, g.nb2) + bt_span(a.s3, g.nb2);
+    (void)n1; (void)n2;
     if (g.cols > cols_max) return false;
     if (pitch > 256 || th + 2 > 256) return false;                   // TMA box limits
     g.Pn0 = round8(g.nb1 * 128);
@@ -1302,7 +1313,8 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     a.pitch_magic = (unsigned)((0x100000000ull + a.pitch - 1) / a.pitch);
     a.tiles_x = (W + bTw - 1) / bTw; a.tiles_y = (H + bTh - 1) / bTh;
     a.s1.nb = g.nb1; a.s2.nb = a.s3.nb = g.nb2;
-    a.s1.col = 0; a.s2.col = g.nb1 * (a.has_s1 ? a.s1.n : 0); a.s3.col = a.s2.col + g.nb2 * a.s2.n;
+    a.s1.cs = bt_cs(a.s1); a.s2.cs = bt_cs(a.s2); a.s3.cs = bt_cs(a.s3);
+    a.s1.col = 0; a.s2.col = a.has_s1 ? bt_span(a.s1, g.nb1) : 0; a.s3.col = a.s2.col + bt_span(a.s2, g.nb2);
     a.tmem_cols = 32;
     while (a.tmem_cols < g.cols) a.tmem_cols *= 2;
     a.Pn0 = g.Pn0; a.Pn1 = g.Pn1; a.Pn2 = g.Pn2;
@@ -1451,7 +1463,7 @@ int fused_block_build(FusedBlock &fb, int kind_, const ConvHost *L, int H, int W
     fb.ok = true;
     if (const char *v = getenv("IMK_BT_VERBOSE"); v && v[0] == '1')
         fprintf(stderr, "[imk] fused block kind=%d %dx%d: %d CTA/SM, A1 x%d, tile %dx%d, M blocks %d/%d, TMEM %d cols, smem %zu B, weights %d B\n", kind, H, W,
-                fb.ctas_per_sm, a.a1_stride ? 2 : 1, a.Th, a.Tw, a.s1.nb, a.s2.nb, a.s3.col + a.s3.nb * a.s3.n, fb.smem, fb.w_bytes);
+                fb.ctas_per_sm, a.a1_stride ? 2 : 1, a.Th, a.Tw, a.s1.nb, a.s2.nb, a.tmem_cols, fb.smem, fb.w_bytes);
     return IMK_OK;
 }
 

@@ -14,6 +14,7 @@ struct BtStage {
     int w_off;                          // byte offset of [tap][kstep][2][n][8] fp16 in the weight region
     int par_off;                        // float offset of bias[n] | scale[n] | shift[n]
     int col;                            // first TMEM column of the stage's accumulator region
+    int cs;                             // TMEM columns between consecutive M blocks (n, or 8 for an n8 stage)
     // 8-channel maps (int(16 * alpha) <= 8, the reference's alpha = 0.5 networks) keep ONE 16-byte plane per position:
     //   kin8: the stage's A operand is a single plane.  K = 16 of an MMA then spans TWO positions: the descriptor's
     //         leading-dimension offset is the distance between two TAPS (f, f + 1: LBO = 16 bytes; (0,2) -> (1,0):
