@@ -54,7 +54,7 @@ constexpr uint32_t kBtSuspendNs = 20000;
 constexpr int kBtSmemMax = 227 * 1024;
 constexpr int kBtSmemMax2 = 112 * 1024;
 constexpr int bt_threads(int ew, int lw) { return (ew + 1 + lw + 1) * 32; }
-constexpr int kBtNumBars = 10 + 3 * kBtMaxBlocks;
+constexpr int kBtNumBars = 12 + 3 * kBtMaxBlocks;
 
 namespace {
 
@@ -461,8 +461,8 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
     // ld_full / ld_empty / tma_full exist per loader buffer: the chain of three has ONE loader buffer (A0), the chain of
     // two loads straight into the double-buffered A1
     uint64_t *ld_full = bars, *ld_empty = bars + 2, *tma_full = bars + 4, *e1_done = bars + 6, *e2_done = bars + 7, *e3_done = bars + 8;
-    uint64_t *o_free = bars + 9;
-    uint64_t *acc1_full = bars + 10, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
+    uint64_t *o_free = bars + 9, *u_full = bars + 10;               // u_full[2]: raw uint8 tiles staged by TMA (FRONT)
+    uint64_t *acc1_full = bars + 12, *acc2_full = acc1_full + kBtMaxBlocks, *acc3_full = acc2_full + kBtMaxBlocks;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kBtNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -470,7 +470,7 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (tid == 0) {
-        for (int j = 0; j < 2; ++j) { mbar_init(&ld_full[j], kBtLoadWarps); mbar_init(&ld_empty[j], 1); mbar_init(&tma_full[j], 1); }
+        for (int j = 0; j < 2; ++j) { mbar_init(&ld_full[j], kBtLoadWarps); mbar_init(&ld_empty[j], 1); mbar_init(&tma_full[j], 1); mbar_init(&u_full[j], 1); }
         mbar_init(o_free, 1 + (a.out_pool ? kBtLoadWarps : 0));      // store warp (+ the loader warps that pool the tile)
         mbar_init(e1_done, kBtEpiWarps); mbar_init(e2_done, kBtEpiWarps); mbar_init(e3_done, kBtEpiWarps);
         for (int b = 0; b < kBtMaxBlocks; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc2_full[b], 1); mbar_init(&acc3_full[b], 1); }
@@ -893,6 +893,26 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             if (lane == 0) mbar_arrive_relaxed(o_free);
         };
         const long long pool_lag = kHasS1 ? 3 : 2;                      // the tile whose E3 runs while this load is in flight
+        // uint8 images (FRONT): the raw haloed tile of image bytes is staged by TMA into one of two shared-memory buffers,
+        // TWO tiles ahead of its use (box rows of (Tw + 2) * c bytes in `u8_panels` panels of <= 256 bytes, zero filled
+        // outside the image), so the loader warps only transform shared memory -> shared memory: no global-load latency
+        // on the per-tile chain (the loader was the most loaded role of the FRONT blocks, one or two exposed latencies per tile).
+        const bool u8_tma = (KIND == 0 || KIND == 3) && a.u8_tma;
+        auto u8_issue = [&](long long ti) {                              // one thread
+            int n_, y0_, x0_;
+            tile_coords(a, (long long)blockIdx.x + ti * gridDim.x, n_, y0_, x0_);
+            const int b = (int)(ti & 1);
+            mbar_expect_tx(&u_full[b], (uint32_t)(a.u8_panels * (a.Th + 2) * a.u8_pw));
+            const uint32_t dst = smem_u32(smem + a.u8_off) + (uint32_t)(b * a.u8_bstride);
+            for (int p = 0; p < a.u8_panels; ++p)
+                tma_load_3d(dst + (uint32_t)(p * a.u8_pstride), &a.tm_in, (((x0_ - 1) * a.in_c) & ~15) + p * a.u8_pw, y0_ - 1, n_, &u_full[b]);   // 16-byte aligned box start
+        };
+        if constexpr (KIND == 0 || KIND == 3) {
+            if (u8_tma && first && n_my > 0) {
+                if (elect_one()) { u8_issue(0); if (n_my > 1) u8_issue(1); }
+                __syncwarp();
+            }
+        }
         for (long long i = 0; i < n_my; ++i) {
             int n, y0, x0;
             tile_coords(a, (long long)blockIdx.x + i * gridDim.x, n, y0, x0);
@@ -905,11 +925,52 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
             if (kHasS1 ? i >= 1 : i >= 2) mbar_wait(&ld_empty[lb], lph ^ 1u);
             LD_T(1);
             if (first) BT_TL(2, i, 1);
+            const uint8_t *U = smem + a.u8_off + (size_t)(i & 1) * a.u8_bstride;
+            const int u8_adj = ((x0 - 1) * a.in_c) & 15;                 // the box starts at the 16-byte boundary at or below the tile's first byte
+            if constexpr (KIND == 0 || KIND == 3) {
+                if (u8_tma) {
+                    if (first && i >= 1 && i + 1 < n_my) {              // U[(i+1)&1] was read for tile i-1: all loader warps are past it
+                        if (elect_one()) {
+                            const long long j = i - 1;
+                            if (kHasS1) mbar_wait(&ld_full[0], (uint32_t)(j & 1));
+                            else mbar_wait(&ld_full[j & 1], (uint32_t)((j >> 1) & 1));
+                            u8_issue(i + 1);
+                        }
+                        __syncwarp();
+                    }
+                    mbar_wait(&u_full[i & 1], (uint32_t)((i >> 1) & 1));
+                }
+            }
             if constexpr (KIND == 0) {
                 // image -> x/255 split into fp16 hi + lo so that the first layer keeps ~22 bits of the input and
                 // of the weights: K slots [hi(c) | lo(c) | hi(c)] against [w_hi | w_hi | w_lo]
                 const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem + a.lut_off);
-                if (!a.in_f32 && (a.in_c == 1 || a.in_c == 3)) {
+                if (u8_tma) {
+                    const int s0 = a.swap_rb ? 2 : 0, s2 = a.swap_rb ? 0 : 2;
+                    for (int f = lt; f < npos; f += NL) {
+                        const int r = (int)__umulhi((unsigned)f, a.pitch_magic), cp_ = f - r * a.pitch;
+                        const int b = cp_ * a.in_c + u8_adj;             // byte of the pixel's first channel in the (aligned-down) box row
+                        auto byte_at = [&](int bb) -> uint32_t {         // a pixel may straddle two panels: locate every byte
+                            const int pnl = (int)__umulhi((unsigned)bb, a.u8_pw_magic);
+                            return U[(size_t)pnl * a.u8_pstride + (size_t)r * a.u8_pw + (bb - pnl * a.u8_pw)];
+                        };
+                        uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+                        if (a.in_c == 1) {                                // outside the image the box holds zeros: x = 0 -> a zero row
+                            const uint32_t e = lut[byte_at(b)];
+                            w0.x = e; w0.y = e & 0xFFFFu;
+                        } else {
+                            const uint32_t e0 = lut[byte_at(b + s0)], e1 = lut[byte_at(b + 1)], e2 = lut[byte_at(b + s2)];
+                            const uint32_t h0 = e0 & 0xFFFFu, h1 = e1 & 0xFFFFu, h2 = e2 & 0xFFFFu;
+                            w0.x = h0 | (h1 << 16);                       // hi0 hi1
+                            w0.y = h2 | (e0 & 0xFFFF0000u);               // hi2 lo0
+                            w0.z = (e1 >> 16) | (e2 & 0xFFFF0000u);       // lo1 lo2
+                            w0.w = h0 | (h1 << 16);                       // hi0 hi1
+                            w1.x = h2;                                    // hi2
+                        }
+                        *reinterpret_cast<uint4 *>(buf + (size_t)f * 16) = w0;
+                        *reinterpret_cast<uint4 *>(buf + ((size_t)Pn + f) * 16) = w1;
+                    }
+                } else if (!a.in_f32 && (a.in_c == 1 || a.in_c == 3)) {
                     const uint8_t *img = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.H * a.W * a.in_c;
                     constexpr int PB = 6;                    // positions in flight per thread
                     for (int f0 = lt; f0 < npos; f0 += PB * NL) {
@@ -981,7 +1042,19 @@ block_tc_kernel(const __grid_constant__ BtArgs a) {
                 // input block through the table: a grayscale uint8 pixel selects the finished fp16 row of the 3x3 stage's
                 // operand (zero outside the image: Conv2D 'same' pads the map the 3x3 reads, unet.py:12)
                 const uint8_t *img = reinterpret_cast<const uint8_t *>(a.in) + (long long)n * a.H * a.W;
-                {
+                if (u8_tma) {
+                    const uint4 *lut4 = reinterpret_cast<const uint4 *>(smem + a.lut_off);
+                    for (int f = lt; f < npos; f += NL) {
+                        const int r = (int)__umulhi((unsigned)f, a.pitch_magic), cp_ = f - r * a.pitch;
+                        const int y = y0 - 1 + r, x = x0 - 1 + cp_;
+                        const bool in = y >= 0 && y < a.H && x >= 0 && x < a.W;      // pixel 0 is NOT a zero row here: test the position
+                        const int bb = cp_ + u8_adj;
+                        const int pnl = (int)__umulhi((unsigned)bb, a.u8_pw_magic);
+                        const uint32_t v = U[(size_t)pnl * a.u8_pstride + (size_t)r * a.u8_pw + (bb - pnl * a.u8_pw)];
+                        for (int kc = 0; kc < KC; ++kc)
+                            *reinterpret_cast<uint4 *>(buf + ((size_t)kc * Pn + f) * 16) = in ? lut4[v * KC + kc] : make_uint4(0, 0, 0, 0);
+                    }
+                } else {
                     const uint4 *lut4 = reinterpret_cast<const uint4 *>(smem + a.lut_off);
                     constexpr int PB = 8;                    // positions in flight per thread
                     for (int f0 = lt; f0 < npos; f0 += PB * NL) {
@@ -1215,6 +1288,24 @@ static inline int bt_cs(const BtStage &st) {
     return (st.n8 && !off) ? 8 : st.n;
 }
 static inline int bt_span(const BtStage &st, int nb) { return nb == 0 ? 0 : bt_cs(st) * nb + (st.n - bt_cs(st)); }
+// Raw uint8 tile staging of the FRONT blocks (see u8_issue in the kernel): box rows of (tw + 2) * c bytes, split into
+// panels of <= 256 bytes (the TMA box limit) whose width is a multiple of 16 bytes AND of c, so that no pixel straddles two.
+struct U8Geom { int pw, panels, pstride, bytes; };
+static bool bt_u8_enabled() {
+    static int off = -1;
+    if (off < 0) { const char *v = getenv("IMK_BT_NO_U8TMA"); off = (v && v[0] == '1') ? 1 : 0; }
+    return !off;
+}
+static U8Geom bt_u8_geom(const BtArgs &a, int th, int tw) {
+    U8Geom u{0, 0, 0, 0};
+    if (!(a.load_kind == 0 || a.load_kind == 3) || !(a.in_c == 1 || a.in_c == 3) || !bt_u8_enabled()) return u;
+    const int L = 16, rb = (tw + 2) * a.in_c + 15, pw_max = 256;     // + 15: the box starts at a 16-byte boundary
+    u.panels = (rb + pw_max - 1) / pw_max;
+    u.pw = ((rb + u.panels - 1) / u.panels + L - 1) / L * L;
+    u.pstride = ((th + 2) * u.pw + 127) / 128 * 128;
+    u.bytes = 2 * u.panels * u.pstride;
+    return u;
+}
 static inline int bt_planes(const BtStage &st) { return st.kin8 ? 1 : st.ksteps * 2; }     // 16-byte planes of the stage's A operand
 
 // shared-memory / TMEM footprint of a candidate tile; plane strides are multiples of 8 positions so that every
@@ -1243,6 +1334,7 @@ static bool bt_geom(const FusedBlock &fb, int th, int tw, int cols_max, size_t s
     off += a1_bufs * (((size_t)g.Pn1 * bt_planes(a.s2) * 16 + 127) / 128 * 128);
     off += (size_t)g.Pn2 * bt_planes(a.s3) * 16;
     if (!a.has_head) off += ((size_t)th * tw * a.out_c * 2 + 127) / 128 * 128;  // head variant: no output staging tile
+    off += (size_t)bt_u8_geom(a, th, tw).bytes;
     if (a.load_kind == 0) off += 1024;
     if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     off += (size_t)kBtNumBars * 8 + 16;
@@ -1325,6 +1417,12 @@ static bool bt_plan(FusedBlock &fb, int H, int W) {
     if (a1_bufs == 1) a.a1_stride = 0;                               // single buffer: both parities alias
     a.a2_off = (int)off; off += (size_t)a.Pn2 * bt_planes(a.s3) * 16;
     a.o_off = (int)off; if (!a.has_head) off += ((size_t)a.Th * a.Tw * a.out_c * 2 + 127) / 128 * 128;
+    {
+        const U8Geom u = bt_u8_geom(a, a.Th, a.Tw);
+        a.u8_off = (int)off; a.u8_pw = u.pw; a.u8_panels = u.panels; a.u8_pstride = u.pstride; a.u8_bstride = u.panels * u.pstride;
+        a.u8_pw_magic = u.pw ? (unsigned)((0x100000000ull + u.pw - 1) / u.pw) : 0u;
+        off += (size_t)u.bytes;
+    }
     a.lut_off = (int)off; if (a.load_kind == 0) off += 1024;
     if (a.load_kind == 3) off += (size_t)256 * a.ld_cp * 2;
     a.bar_off = (int)off; off += (size_t)kBtNumBars * 8 + 16;        // everything in [a0_off, bar_off) starts zeroed
@@ -1495,6 +1593,21 @@ int fused_block_launch(const FusedBlock &fb, const void *in, const __half *in_lo
     if (out_pool && !fused_block_can_pool(fb)) { set_error("fused block: the tile cannot carry the 2x2 max-pool"); return IMK_EINVAL; }
     a.n_tiles = (long long)n * a.tiles_x * a.tiles_y;
     if (a.n_tiles <= 0) return IMK_OK;
+    a.u8_tma = 0;
+    if ((a.load_kind == 0 || a.load_kind == 3) && a.u8_panels > 0 && !in_f32 && (a.W * a.in_c) % 16 == 0) {
+        // the image as uint8 [n][H][W*c]; boxes {panel width, Th + 2, 1}, zero filled outside the image
+        EncodeTiledFn fn = encode_tiled_fn();
+        if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return IMK_ECUDA; }
+        const cuuint64_t dims[3] = {(cuuint64_t)a.W * a.in_c, (cuuint64_t)a.H, (cuuint64_t)n};
+        const cuuint64_t strides[2] = {(cuuint64_t)a.W * a.in_c, (cuuint64_t)a.H * a.W * a.in_c};
+        const cuuint32_t box[3] = {(cuuint32_t)a.u8_pw, (cuuint32_t)(a.Th + 2), 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = fn(&a.tm_in, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(in), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (uint8 image) failed (%d) for [%lld,%d,%d] box %dx%d", (int)r, (long long)n, a.H, a.W * a.in_c, a.u8_pw, a.Th + 2); return IMK_ECUDA; }
+        a.u8_tma = 1;
+    }
     if (a.load_kind == 1 || a.load_kind == 2) {
         a.tm_flat8 = (a.ld_cp == 8 && a.pitch <= 128) ? 1 : 0;
         if (const char *v = getenv("IMK_BT_NO_FLAT8"); v && v[0] == '1') a.tm_flat8 = 0;

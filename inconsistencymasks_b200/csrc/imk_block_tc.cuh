@@ -46,6 +46,9 @@ struct BtArgs {
     int o_off;                          // output staging tile [Th][Tw][out_c] fp16
     int out_c;                          // channels per pixel of the output map in HBM (s3.n, or 8 when s3.n8)
     int lut_off;                        // FRONT: 256-entry table of x/255 as fp16 hi | lo << 16
+    // FRONT, uint8 images: raw tile staging by TMA (u8_issue): two buffers of `u8_panels` panels [Th + 2][u8_pw] bytes
+    int u8_tma, u8_off, u8_pw, u8_panels, u8_pstride, u8_bstride;
+    unsigned u8_pw_magic;               // ceil(2^32 / u8_pw)
     int tm_flat8;                       // tm_in describes an 8-channel map as uint64 [N][H][2W] (contiguous tile rows)
     alignas(64) CUtensorMap tm_in;      // TMA map (ENC / DEC): {8 ch, pitch, Th + 2, 1} boxes of the fp16 NHWC input / skip map
     // Epilogue constants, read as constant-bank operands (no loads): the BN scale is folded into the weights, so a
