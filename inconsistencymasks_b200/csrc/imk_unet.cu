@@ -488,6 +488,20 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
                         // numerators more than 2^-22 apart (relative) cannot round to the same quotient, so the first
                         // maximum of e is the first maximum of p unless another numerator is that close to it (or a
                         // NaN is around) -- only then the exact probabilities are formed, with pixel_activation's ops
+                        // First, on the LOGITS: exp is monotonic and the winner's numerator is exp(0) = 1 exactly, so a runner-up
+                        // more than 1e-5 below the winner has a numerator < 1 - 9.7e-6 (with __expf's 2-ulp error) and its
+                        // rounded quotient is strictly smaller: the first maximum of the logits IS np.argmax of the
+                        // probabilities, and none of the K exponentials is needed.  NaN / infinite logits (the probabilities are
+                        // all NaN then) and closer calls take the numerator path below.
+                        float lbest = p[0], lsecond = -INFINITY, lsum = p[0];
+#pragma unroll
+                        for (int k = 1; k < KMAX; ++k) {
+                            lsum += p[k];
+                            if (p[k] > lbest) { lsecond = lbest; lbest = p[k]; arg = k; } else lsecond = fmaxf(lsecond, p[k]);
+                        }
+                        fast_arg = (lbest - lsecond > 1e-5f) && (lsum == lsum) && (lbest < INFINITY);
+                        if (!fast_arg) {
+                        arg = 0;
                         float mx = p[0];
 #pragma unroll
                         for (int k = 1; k < KMAX; ++k) mx = fmaxf(mx, p[k]);
@@ -505,6 +519,7 @@ ensemble_im_kernel(EnsPtrs ens, int M, int c1p_, int K_, int act, float thr, int
                         if (!fast_arg) {
 #pragma unroll
                             for (int k = 0; k < KMAX; ++k) p[k] = __fdiv_rn(p[k], sum);
+                        }
                         }
                     } else if (!kMulticlass && act == IMK_ACT_SIGMOID && dstar > 0.f) {
                         // threshold of the sigmoid without its division: RN(1 / d) is monotonic in d = 1 + exp(-z), so
