@@ -23,7 +23,9 @@ import numpy as np
 
 from ._lib import lib, check, AugParams
 
-__all__ = ["augment_image_and_mask", "augment_image_and_masks", "draw_params", "augment_batch"]
+__all__ = ["augment_image_and_mask", "augment_image_and_masks", "draw_params", "augment_batch",
+           "create_augment_images_and_masks_ISIC_2018", "create_augment_images_and_masks_hela",
+           "create_augment_images_and_masks_multiclass"]
 
 
 def draw_params(brightness_range_alpha=(0.5, 1.5), brightness_range_beta=(-25, 25), max_blur=3, max_noise=25, free_rotation=True):
@@ -89,3 +91,88 @@ def augment_image_and_mask(image, mask, brightness_range_alpha=(0.5, 1.5), brigh
     out, masks = _one(image, [mask], dict(brightness_range_alpha=brightness_range_alpha, brightness_range_beta=brightness_range_beta,
                                           max_blur=max_blur, max_noise=max_noise, free_rotation=free_rotation))
     return out, masks[0]
+
+
+# ------------------------------------------------------------------------------------ per-directory drivers (IM+ step)
+_SAMPLES_PER_BATCH = 2048
+
+
+def _geometry_only(p):
+    q = AugParams()
+    q.flip_v, q.flip_h, q.rot = p.flip_v, p.flip_h, p.rot
+    return q
+
+
+def _augment_directory(dirs_in, dirs_out, num_images, copy_org, kw):
+    """dirs_in[0] holds the images, the others their masks (same file names); every file is read with ``cv2.imread``'s
+    default flags like the reference (3-channel BGR), augmented ``num_images`` times and written as ``<stem>_aug_<n>.png``.
+    The decisions are drawn per (file, n) in the reference's loop order; the pixels of a whole batch of samples are
+    computed on the device (image: all operations; masks: the geometry only)."""
+    import os
+    import shutil
+    from concurrent.futures import ThreadPoolExecutor
+    import cv2
+    from . import functions as F
+    for d in dirs_out:
+        os.makedirs(d, exist_ok=True)
+    names = os.listdir(dirs_in[0])
+    if copy_org:
+        for nm in names:
+            for di, do in zip(dirs_in, dirs_out):
+                shutil.copy(os.path.join(di, nm), os.path.join(do, nm))
+    if not names or num_images <= 0:
+        return
+    threads = max(4, min(32, os.cpu_count() or 4))
+    per_batch = max(1, _SAMPLES_PER_BATCH // num_images)
+    with ThreadPoolExecutor(threads) as io:
+        for b0 in range(0, len(names), per_batch):
+            bn = names[b0:b0 + per_batch]
+            stacks = [list(io.map(lambda nm, d=d: cv2.imread(os.path.join(d, nm)), bn)) for d in dirs_in]
+            params = [draw_params(**kw) for _ in bn for _ in range(num_images)]        # file-major, n inner: functions.py:2604-2609
+            # group by shape (a batch on the device shares H x W)
+            shapes = {}
+            for i, im in enumerate(stacks[0]):
+                shapes.setdefault(im.shape, []).append(i)
+            for shape, idx in shapes.items():
+                rep = np.repeat(np.asarray(idx), num_images)
+                ps = [params[i * num_images + n] for i in idx for n in range(num_images)]
+                outs = []
+                for k, st in enumerate(stacks):
+                    batch = F._dev(np.ascontiguousarray(np.stack([st[i] for i in rep])))
+                    out, _ = augment_batch(batch, None, ps if k == 0 else [_geometry_only(p) for p in ps])
+                    outs.append(out.cpu().numpy())
+                jobs = []
+                for j, i in enumerate(rep):
+                    n = j % num_images
+                    for k, do in enumerate(dirs_out):
+                        jobs.append((os.path.join(do, f"{bn[i][:-4]}_aug_{n}.png"), outs[k][j]))
+                list(io.map(lambda job: cv2.imwrite(job[0], job[1]), jobs))
+
+
+def create_augment_images_and_masks_ISIC_2018(images_path, masks_path, main_output_path, num_images=9, copy_org=True,
+                                              brightness_range_alpha=(0.5, 1.5), brightness_range_beta=(-25, 25), max_blur=3, max_noise=25,
+                                              free_rotation=True):
+    """functions.py:2567-2609."""
+    import os
+    _augment_directory([images_path, masks_path], [os.path.join(main_output_path, "images"), os.path.join(main_output_path, "masks")],
+                       num_images, copy_org, dict(brightness_range_alpha=brightness_range_alpha, brightness_range_beta=brightness_range_beta,
+                                                  max_blur=max_blur, max_noise=max_noise, free_rotation=free_rotation))
+
+
+def create_augment_images_and_masks_multiclass(images_path, masks_path, main_output_path, num_images=9, copy_org=True, free_rotation=False,
+                                               brightness_range_alpha=(0.5, 1.5), brightness_range_beta=(-25, 25), max_blur=3, max_noise=25):
+    """functions.py:2678-2722."""
+    import os
+    _augment_directory([images_path, masks_path], [os.path.join(main_output_path, "images"), os.path.join(main_output_path, "masks")],
+                       num_images, copy_org, dict(brightness_range_alpha=brightness_range_alpha, brightness_range_beta=brightness_range_beta,
+                                                  max_blur=max_blur, max_noise=max_noise, free_rotation=free_rotation))
+
+
+def create_augment_images_and_masks_hela(main_input_path, main_output_path, num_images=9, copy_org=True, free_rotation=True,
+                                         brightness_range_alpha=(0.7, 1.3), brightness_range_beta=(-15, 15), max_blur=3, max_noise=25):
+    """functions.py:2613-2675."""
+    import os
+    subs = ("brightfield", "alive", "dead", "mod_position")
+    _augment_directory([os.path.join(main_input_path, s) for s in subs], [os.path.join(main_output_path, s) for s in subs],
+                       num_images, copy_org, dict(brightness_range_alpha=brightness_range_alpha, brightness_range_beta=brightness_range_beta,
+                                                  max_blur=max_blur, max_noise=max_noise, free_rotation=free_rotation))

@@ -50,11 +50,13 @@ __all__ = [
 
 from .evaluation import (benchmark_ISIC2018, benchmark_hela, benchmark_multiclass, get_IoU_binary, get_IoU_multi_unique,  # noqa: E402,F401
                          pixel_accuracy, dice_score_numpy_binary, mod_pos_size, get_cell_count, convert_class_to_color_mask)
-from .augment import augment_image_and_mask, augment_image_and_masks  # noqa: E402,F401
+from .augment import (augment_image_and_mask, augment_image_and_masks, create_augment_images_and_masks_ISIC_2018,  # noqa: E402,F401
+                      create_augment_images_and_masks_hela, create_augment_images_and_masks_multiclass)
 
 __all__ += ["benchmark_ISIC2018", "benchmark_hela", "benchmark_multiclass", "get_IoU_binary", "get_IoU_multi_unique", "pixel_accuracy",
             "dice_score_numpy_binary", "mod_pos_size", "get_cell_count", "convert_class_to_color_mask",
-            "augment_image_and_mask", "augment_image_and_masks"]
+            "augment_image_and_mask", "augment_image_and_masks", "create_augment_images_and_masks_ISIC_2018",
+            "create_augment_images_and_masks_hela", "create_augment_images_and_masks_multiclass"]
 
 
 def _torch():

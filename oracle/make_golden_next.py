@@ -31,6 +31,7 @@ WANTED = {
     "augment_image_and_mask", "augment_image_and_masks", "add_noise", "add_noise_and_blur",
     "benchmark_ISIC2018", "benchmark_hela", "benchmark_multiclass",
     "get_pos_contours", "get_min_dist", "mod_pos_size", "get_cell_count", "convert_class_to_color_mask",
+    "create_augment_images_and_masks_ISIC_2018", "create_augment_images_and_masks_hela", "create_augment_images_and_masks_multiclass",
 }
 
 
@@ -39,7 +40,8 @@ def load_reference():
     body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in WANTED]
     missing = WANTED - {n.name for n in body}
     assert not missing, missing
-    ns = {"np": np, "cv2": cv2, "os": os, "io": io, "contextlib": contextlib, "random": random,
+    import shutil
+    ns = {"np": np, "cv2": cv2, "os": os, "io": io, "contextlib": contextlib, "random": random, "shutil": shutil,
           "tqdm": lambda it, *a, **k: it}
     exec(compile(ast.Module(body=body, type_ignores=[]), REF, "exec"), ns)
     return ns
@@ -119,6 +121,31 @@ def main():
         store[f"a{seed}_out"], store[f"a{seed}_mask_out"] = out, mask_out
         cases.append((seed, int(square), int(seed % 4 == 3)))
     store["cases"] = np.array(cases, np.int64)
+    # the per-directory drivers: ONE file per directory (os.listdir order must not matter), several augmentations of it
+    with tempfile.TemporaryDirectory() as tmp:
+        img = rng.integers(0, 256, size=(40, 40, 3), dtype=np.uint8)
+        msk = (rng.random((40, 40)) > 0.5).astype(np.uint8) * 255
+        for d, m in (("i", img), ("m", msk)):
+            os.makedirs(os.path.join(tmp, d)); cv2.imwrite(os.path.join(tmp, d, "one.png"), m)
+        random.seed(77); np.random.seed(78)
+        ns["create_augment_images_and_masks_ISIC_2018"](os.path.join(tmp, "i"), os.path.join(tmp, "m"), os.path.join(tmp, "o"), 5, True, max_noise=0)
+        store["drv_isic_image"], store["drv_isic_mask"] = img, msk
+        for n in range(5):
+            store[f"drv_isic_out_{n}"] = cv2.imread(os.path.join(tmp, "o", "images", f"one_aug_{n}.png"))
+            store[f"drv_isic_mask_out_{n}"] = cv2.imread(os.path.join(tmp, "o", "masks", f"one_aug_{n}.png"))
+        store["drv_isic_copy"] = cv2.imread(os.path.join(tmp, "o", "images", "one.png"))
+        bf = rng.integers(0, 256, size=(32, 32), dtype=np.uint8)
+        hm = [(rng.random((32, 32)) > 0.6).astype(np.uint8) * 255 for _ in range(3)]
+        for d, m in zip(("brightfield", "alive", "dead", "mod_position"), [bf] + hm):
+            os.makedirs(os.path.join(tmp, "h", d)); cv2.imwrite(os.path.join(tmp, "h", d, "c.png"), m)
+        random.seed(79); np.random.seed(80)
+        ns["create_augment_images_and_masks_hela"](os.path.join(tmp, "h"), os.path.join(tmp, "ho"), 4, False, max_noise=0)
+        store["drv_hela_bf"] = bf
+        for j, m in enumerate(hm):
+            store[f"drv_hela_m{j}"] = m
+        for n in range(4):
+            for d in ("brightfield", "alive", "dead", "mod_position"):
+                store[f"drv_hela_{d}_{n}"] = cv2.imread(os.path.join(tmp, "ho", d, f"c_aug_{n}.png"))
     np.savez_compressed(os.path.join(OUT, "augment.npz"), **store)
 
     # ---- benchmark_* drivers -------------------------------------------------------------------------------

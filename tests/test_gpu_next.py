@@ -346,3 +346,42 @@ def test_evalnet_forward_vs_fp32_oracle(h, w, ca, cb, alpha, heads):
     from inconsistencymasks_b200.weights import evalnet_plan
     assert model.count_params() == sum((it[1] ** 2 * it[2] * it[3] + it[3]) if it[0] == "conv" else (4 * it[1] if it[0] == "bn" else it[1] * it[2] + it[2])
                                        for it in evalnet_plan(ca, cb, alpha, heads))
+
+
+def test_augment_directory_drivers_vs_reference_golden(A, tmp_path):
+    """create_augment_images_and_masks_ISIC_2018 / _hela on the directories the reference was run on (one file each, so that
+    os.listdir order cannot matter), same module seeds, max_noise = 0: every written PNG is the reference's."""
+    z = np.load(os.path.join(G, "augment.npz"))
+    i_dir, m_dir, o_dir = tmp_path / "i", tmp_path / "m", tmp_path / "o"
+    i_dir.mkdir(); m_dir.mkdir()
+    cv2.imwrite(str(i_dir / "one.png"), z["drv_isic_image"]); cv2.imwrite(str(m_dir / "one.png"), z["drv_isic_mask"])
+    random.seed(77); np.random.seed(78)
+    A.create_augment_images_and_masks_ISIC_2018(str(i_dir), str(m_dir), str(o_dir), 5, True, max_noise=0)
+    for n in range(5):
+        same(cv2.imread(str(o_dir / "images" / f"one_aug_{n}.png")), z[f"drv_isic_out_{n}"])
+        same(cv2.imread(str(o_dir / "masks" / f"one_aug_{n}.png")), z[f"drv_isic_mask_out_{n}"])
+    same(cv2.imread(str(o_dir / "images" / "one.png")), z["drv_isic_copy"])
+    h_in, h_out = tmp_path / "h", tmp_path / "ho"
+    for d, key in (("brightfield", "drv_hela_bf"), ("alive", "drv_hela_m0"), ("dead", "drv_hela_m1"), ("mod_position", "drv_hela_m2")):
+        (h_in / d).mkdir(parents=True)
+        cv2.imwrite(str(h_in / d / "c.png"), z[key])
+    random.seed(79); np.random.seed(80)
+    A.create_augment_images_and_masks_hela(str(h_in), str(h_out), 4, False, max_noise=0)
+    for n in range(4):
+        for d in ("brightfield", "alive", "dead", "mod_position"):
+            same(cv2.imread(str(h_out / d / f"c_aug_{n}.png")), z[f"drv_hela_{d}_{n}"])
+    assert not (h_out / "brightfield" / "c.png").exists()                      # copy_org=False
+    # many files, noise on: right number of outputs, masks only moved (same multiset of values per file)
+    many_i, many_m, many_o = tmp_path / "mi", tmp_path / "mm", tmp_path / "mo"
+    many_i.mkdir(); many_m.mkdir()
+    rng = np.random.default_rng(3)
+    for k in range(23):
+        cv2.imwrite(str(many_i / f"f{k:02d}.png"), rng.integers(0, 256, size=(64, 64, 3), dtype=np.uint8))
+        cv2.imwrite(str(many_m / f"f{k:02d}.png"), rng.integers(0, 9, size=(64, 64), dtype=np.uint8))
+    A.create_augment_images_and_masks_multiclass(str(many_i), str(many_m), str(many_o), 3, True)
+    assert len(os.listdir(many_o / "images")) == 23 * 4 and len(os.listdir(many_o / "masks")) == 23 * 4
+    for k in (0, 11, 22):
+        src = cv2.imread(str(many_m / f"f{k:02d}.png"))
+        for n in range(3):
+            out = cv2.imread(str(many_o / "masks" / f"f{k:02d}_aug_{n}.png"))
+            assert np.array_equal(np.bincount(out.ravel(), minlength=9), np.bincount(src.ravel(), minlength=9))
