@@ -53,7 +53,11 @@ from .evaluation import (benchmark_ISIC2018, benchmark_hela, benchmark_multiclas
 from .augment import (augment_image_and_mask, augment_image_and_masks, create_augment_images_and_masks_ISIC_2018,  # noqa: E402,F401
                       create_augment_images_and_masks_hela, create_augment_images_and_masks_multiclass)
 
-__all__ += ["benchmark_ISIC2018", "benchmark_hela", "benchmark_multiclass", "get_IoU_binary", "get_IoU_multi_unique", "pixel_accuracy",
+from .impp import (create_augment_images_and_masks_with_evalnet_ensemble_binary,  # noqa: E402,F401
+                   create_augment_images_and_masks_with_evalnet_ensemble_multiclass)
+
+__all__ += ["create_augment_images_and_masks_with_evalnet_ensemble_binary", "create_augment_images_and_masks_with_evalnet_ensemble_multiclass",
+            "benchmark_ISIC2018", "benchmark_hela", "benchmark_multiclass", "get_IoU_binary", "get_IoU_multi_unique", "pixel_accuracy",
             "dice_score_numpy_binary", "mod_pos_size", "get_cell_count", "convert_class_to_color_mask",
             "augment_image_and_mask", "augment_image_and_masks", "create_augment_images_and_masks_ISIC_2018",
             "create_augment_images_and_masks_hela", "create_augment_images_and_masks_multiclass"]

@@ -11,6 +11,8 @@ unmodified under NumPy / cv2; only inputs and the outputs the reference computed
                    (max_noise = 0: the deterministic part; the noise has distributional parity only)
   benchmarks.npz   benchmark_ISIC2018 / benchmark_hela / benchmark_multiclass on synthetic directories with replayed
                    probability maps                                                                 functions.py:1078-1339
+  impp.npz         create_augment_images_and_masks_with_evalnet_ensemble_binary / _multiclass with replayed EvalNet scores:
+                   copies written per file                                                           functions.py:5684-6054
 """
 import ast
 import contextlib
@@ -32,6 +34,7 @@ WANTED = {
     "benchmark_ISIC2018", "benchmark_hela", "benchmark_multiclass",
     "get_pos_contours", "get_min_dist", "mod_pos_size", "get_cell_count", "convert_class_to_color_mask",
     "create_augment_images_and_masks_ISIC_2018", "create_augment_images_and_masks_hela", "create_augment_images_and_masks_multiclass",
+    "create_augment_images_and_masks_with_evalnet_ensemble_binary", "create_augment_images_and_masks_with_evalnet_ensemble_multiclass",
 }
 
 
@@ -217,7 +220,65 @@ def main():
         for d in ("alive", "dead", "mod_position"):
             store[f"hela_pred_{d}"] = np.stack([cv2.imread(os.path.join(pdir, d, f"c_{i:03d}.png"), 0) for i in range(7)])
     np.savez_compressed(os.path.join(OUT, "benchmarks.npz"), **store)
-    print("wrote", [f for f in sorted(os.listdir(OUT)) if f in ("metrics.npz", "augment.npz", "benchmarks.npz")])
+
+    # ---- IM++ drivers: EvalNet scores -> number of augmented copies (functions.py:5684-5759, 5946-6054) ------------------
+    # replayed EvalNet outputs; augmentation reduced to the horizontal flip (no blur / noise / brightness change, no free
+    # rotation) so that the outputs do not depend on the order in which os.listdir hands the files to the RNG
+    class ScoreNet:
+        def __init__(self):
+            self.table = {}
+
+        def add(self, image, out):
+            self.table[np.ascontiguousarray(image).astype(np.uint8).tobytes()] = out
+
+        def predict(self, x, *a, **k):
+            a0 = np.asarray(x[0])
+            outs = [self.table[np.ascontiguousarray(a0[i]).astype(np.uint8).tobytes()] for i in range(a0.shape[0])]
+            if isinstance(outs[0], tuple):
+                return [np.stack([o[0] for o in outs]), np.stack([o[1] for o in outs])]
+            return np.stack(outs)
+
+    store = {}
+    h = w = 32
+    rng2 = np.random.default_rng(4242)
+    with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()):
+        n = 9
+        os.makedirs(os.path.join(tmp, "b", "images")); os.makedirs(os.path.join(tmp, "b", "masks"))
+        nets = [ScoreNet(), ScoreNet()]
+        imgs, msks, scores = [], [], []
+        for i in range(n):
+            img = rng2.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+            msk = (rng2.random((h, w)) > 0.5).astype(np.uint8) * 255
+            sc = np.array([[0.05 + 0.11 * i]], np.float32)[0]              # spans below min .. above max
+            cv2.imwrite(os.path.join(tmp, "b", "images", f"p{i}.png"), img); cv2.imwrite(os.path.join(tmp, "b", "masks", f"p{i}.png"), msk)
+            for k, net in enumerate(nets):
+                net.add(cv2.cvtColor(img, cv2.COLOR_BGR2RGB), sc + np.float32(0.02 * k))
+            imgs.append(img); msks.append(msk); scores.append(sc)
+        ns["create_augment_images_and_masks_with_evalnet_ensemble_binary"](nets, h, w, 3, 0.3, 0.8, os.path.join(tmp, "b"), os.path.join(tmp, "bo"),
+                                                                           (1.0, 1.0), (0.0, 0.0), 0, 0, False, True)
+        store["b_images"], store["b_masks"], store["b_scores"] = np.stack(imgs), np.stack(msks), np.stack(scores)
+        store["b_counts"] = np.array([len([f for f in os.listdir(os.path.join(tmp, "bo", "images")) if f.startswith(f"p{i}___")]) for i in range(n)], np.int64)
+        k = 5
+        os.makedirs(os.path.join(tmp, "m", "images")); os.makedirs(os.path.join(tmp, "m", "masks"))
+        nets = [ScoreNet(), ScoreNet(), ScoreNet()]
+        imgs, msks, ious, dets = [], [], [], []
+        for i in range(n):
+            img = rng2.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+            msk = rng2.integers(0, k, size=(h, w), dtype=np.uint8)
+            iou = rng2.random(k).astype(np.float32) * (0.2 + 0.1 * i)
+            det = (rng2.random(k) > 0.4).astype(np.float32) * 0.9
+            if i == 3:
+                det[:] = 0.1                                               # no class passes the detection check -> mIoU 0
+            cv2.imwrite(os.path.join(tmp, "m", "images", f"q{i}.png"), img); cv2.imwrite(os.path.join(tmp, "m", "masks", f"q{i}.png"), msk)
+            for j, net in enumerate(nets):
+                net.add(cv2.cvtColor(img, cv2.COLOR_BGR2RGB), (iou + np.float32(0.01 * j), det))
+            imgs.append(img); msks.append(msk); ious.append(iou); dets.append(det)
+        ns["create_augment_images_and_masks_with_evalnet_ensemble_multiclass"](nets, h, w, 3, k, 0.2, 0.6, os.path.join(tmp, "m"), os.path.join(tmp, "mo"),
+                                                                               (1.0, 1.0), (0.0, 0.0), 0, 0, False, True)
+        store["m_images"], store["m_masks"], store["m_ious"], store["m_dets"] = np.stack(imgs), np.stack(msks), np.stack(ious), np.stack(dets)
+        store["m_counts"] = np.array([len([f for f in os.listdir(os.path.join(tmp, "mo", "images")) if f.startswith(f"q{i}___")]) for i in range(n)], np.int64)
+    np.savez_compressed(os.path.join(OUT, "impp.npz"), **store)
+    print("wrote", [f for f in sorted(os.listdir(OUT)) if f in ("metrics.npz", "augment.npz", "benchmarks.npz", "impp.npz")])
 
 
 if __name__ == "__main__":

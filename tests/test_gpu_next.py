@@ -385,3 +385,77 @@ def test_augment_directory_drivers_vs_reference_golden(A, tmp_path):
         for n in range(3):
             out = cv2.imread(str(many_o / "masks" / f"f{k:02d}_aug_{n}.png"))
             assert np.array_equal(np.bincount(out.ravel(), minlength=9), np.bincount(src.ravel(), minlength=9))
+
+
+class ScoreNet:
+    """Replays stored EvalNet outputs by image content, a batch at a time."""
+
+    def __init__(self):
+        self.table = {}
+
+    def add(self, image, out):
+        self.table[np.ascontiguousarray(image).astype(np.uint8).tobytes()] = out
+
+    def predict(self, x, *a, **k):
+        a0 = np.asarray(x[0])
+        outs = [self.table[np.ascontiguousarray(a0[i]).astype(np.uint8).tobytes()] for i in range(a0.shape[0])]
+        if isinstance(outs[0], tuple):
+            return [np.stack([o[0] for o in outs]), np.stack([o[1] for o in outs])]
+        return np.stack(outs)
+
+
+def test_impp_drivers_vs_reference_golden(F, tmp_path):
+    """IM++: EvalNet ensemble score -> number of augmented copies per file, as the reference decided on the same replayed
+    scores; each copy is the file itself or its horizontal flip (augmentation reduced to the flip in this run), image and
+    mask moved together."""
+    z = np.load(os.path.join(G, "impp.npz"))
+    h = w = 32
+    # binary (ISIC)
+    root, out = tmp_path / "b", tmp_path / "bo"
+    (root / "images").mkdir(parents=True); (root / "masks").mkdir()
+    nets = [ScoreNet(), ScoreNet()]
+    n = len(z["b_images"])
+    for i in range(n):
+        cv2.imwrite(str(root / "images" / f"p{i}.png"), z["b_images"][i]); cv2.imwrite(str(root / "masks" / f"p{i}.png"), z["b_masks"][i])
+        for k, net in enumerate(nets):
+            net.add(cv2.cvtColor(z["b_images"][i], cv2.COLOR_BGR2RGB), z["b_scores"][i] + np.float32(0.02 * k))
+    F.create_augment_images_and_masks_with_evalnet_ensemble_binary(nets, h, w, 3, 0.3, 0.8, str(root), str(out), (1.0, 1.0), (0.0, 0.0), 0, 0, False, True)
+    counts = [len([f for f in os.listdir(out / "images") if f.startswith(f"p{i}___")]) for i in range(n)]
+    assert counts == list(z["b_counts"])
+    for i in range(n):
+        for j in range(counts[i]):
+            im, mk = cv2.imread(str(out / "images" / f"p{i}___{j}.png")), cv2.imread(str(out / "masks" / f"p{i}___{j}.png"), 0)
+            flipped = np.array_equal(im, z["b_images"][i][:, ::-1])
+            assert flipped or np.array_equal(im, z["b_images"][i])
+            same(mk, np.ascontiguousarray(z["b_masks"][i][:, ::-1]) if flipped else z["b_masks"][i])
+    # multiclass (SUIM / Cityscapes)
+    k = z["m_ious"].shape[1]
+    root, out = tmp_path / "m", tmp_path / "mo"
+    (root / "images").mkdir(parents=True); (root / "masks").mkdir()
+    nets = [ScoreNet(), ScoreNet(), ScoreNet()]
+    for i in range(n):
+        cv2.imwrite(str(root / "images" / f"q{i}.png"), z["m_images"][i]); cv2.imwrite(str(root / "masks" / f"q{i}.png"), z["m_masks"][i])
+        for j, net in enumerate(nets):
+            net.add(cv2.cvtColor(z["m_images"][i], cv2.COLOR_BGR2RGB), (z["m_ious"][i] + np.float32(0.01 * j), z["m_dets"][i]))
+    F.create_augment_images_and_masks_with_evalnet_ensemble_multiclass(nets, h, w, 3, k, 0.2, 0.6, str(root), str(out), (1.0, 1.0), (0.0, 0.0), 0, 0, False, True)
+    counts = [len([f for f in os.listdir(out / "images") if f.startswith(f"q{i}___")]) for i in range(n)]
+    assert counts == list(z["m_counts"])
+
+
+def test_impp_driver_with_b200_evalnets(F, tmp_path):
+    """The same driver with real EvalNets on the device: runs end to end, 1..5 copies per file, masks keep their classes."""
+    from inconsistencymasks_b200 import evalnet as EV
+    h = w = 64; k = 4
+    rng = np.random.default_rng(8)
+    root, out = tmp_path / "in", tmp_path / "out"
+    (root / "images").mkdir(parents=True); (root / "masks").mkdir()
+    for i in range(12):
+        cv2.imwrite(str(root / "images" / f"s{i}.png"), rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8))
+        cv2.imwrite(str(root / "masks" / f"s{i}.png"), rng.integers(0, k, size=(h, w), dtype=np.uint8))
+    nets = [EV.get_evalnet_miou(h, w, 3, k, 1.0, seed=s) for s in (1, 2)]
+    F.create_augment_images_and_masks_with_evalnet_ensemble_multiclass(nets, h, w, 3, k, 0.3, 0.7, str(root), str(out))
+    for i in range(12):
+        c = len([f for f in os.listdir(out / "images") if f.startswith(f"s{i}___")])
+        assert 1 <= c <= 5 and c == len([f for f in os.listdir(out / "masks") if f.startswith(f"s{i}___")])
+        src = cv2.imread(str(root / "masks" / f"s{i}.png"), 0)
+        assert np.array_equal(np.bincount(cv2.imread(str(out / "masks" / f"s{i}___0.png"), 0).ravel(), minlength=k), np.bincount(src.ravel(), minlength=k))
