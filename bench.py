@@ -411,26 +411,28 @@ def measured_traffic(key, images_per_launch):
         return None
 
 
-def time_resident(wl, steps, warmup, world, barrier, stats=None):
-    """K timed steps between two device events, barrier + synchronize on both sides; returns ms for all K steps."""
-    import torch
+def resident_step(wl, world, stats):
+    """One step of the resident-input measurement: the fused ensemble call + the coverage statistic (row a10)."""
     import torch.distributed as dist
+    wl.step()
+    if stats is not None:
+        stats[0] = wl.im_size.sum(); stats[1] = wl.pred_size.sum(); stats[2] = wl.N
+        if world > 1:
+            dist.all_reduce(stats)          # the one collective: coverage statistics
 
-    def step():
-        wl.step()
-        if stats is not None:
-            stats[0] = wl.im_size.sum(); stats[1] = wl.pred_size.sum(); stats[2] = wl.N
-            if world > 1:
-                dist.all_reduce(stats)          # the one collective: coverage statistics (row a10)
 
+def time_resident(wl, steps, warmup, world, barrier, stats=None):
+    """K timed steps between two device events, barrier + synchronize on both sides; returns ms for all K steps.
+    Warm-up steps run the SAME step (including the statistic's small reductions: their first launch loads a module)."""
+    import torch
     for _ in range(warmup):
-        step()
+        resident_step(wl, world, stats)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(steps):
-        step()
+        resident_step(wl, world, stats)
     e1.record()
     barrier()
     return e0.elapsed_time(e1)
@@ -518,14 +520,14 @@ def run_b200(args, name, cfg, rank, local_rank, world):
     stats = torch.zeros(3, dtype=torch.int64, device=dev)
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
-        wl.step()
+        resident_step(wl, world, stats)     # the step that is timed below, statistic included
     # settle: a fresh process on a fresh box sometimes runs its first few steps ~20 % slow (clock ramp, first-touch of the
     # workspaces); keep warming (untimed, at most 8 more steps, counted in `warmup`) until two consecutive steps agree to 2 %
     torch.cuda.synchronize()
     prev = None
     for _ in range(8):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); wl.step(); e1.record()
+        e0.record(); resident_step(wl, world, stats); e1.record()
         torch.cuda.synchronize()
         cur = allmax(e0.elapsed_time(e1))
         warmup += 1
