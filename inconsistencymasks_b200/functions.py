@@ -98,6 +98,10 @@ def _masks_to_im(pred_masks, multiclass):
     stack = np.stack([np.asarray(m) for m in pred_masks], axis=0)
     out_shape = np.squeeze(np.empty(stack.shape[1:], np.uint8)).shape
     m = stack.shape[0]
+    if stack.dtype.kind == "f" and not np.array_equal(stack, np.trunc(stack)):
+        # the reference sums the masks in their own dtype (functions.py:3108); only integer-valued masks (0/1 decisions,
+        # class ids) have a defined IM, so fractional values are refused instead of being truncated silently
+        raise ValueError("pred_masks_to_im_*: masks must hold integer values")
     flat = np.ascontiguousarray(stack.reshape(m, -1).astype(np.int64, copy=False))
     p = flat.shape[1]
     d_masks = _dev(flat)
