@@ -36,8 +36,8 @@ def _nvcc() -> str:
 
 def _digest(paths) -> str:
     h = hashlib.sha256()
-    for p in sorted(paths):
-        h.update(p.encode())
+    for p in sorted(paths, key=os.path.basename):
+        h.update(os.path.basename(p).encode())      # names, not absolute paths: the digest is the same wherever the tree is mounted
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
