@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import lib, check
 from .weights import evalnet_plan, init_evalnet_weights
 
-__all__ = ["B200EvalNet", "get_evalnet", "get_evalnet_miou", "weights_from_keras", "evalnet_plan", "init_evalnet_weights"]
+__all__ = ["B200EvalNet", "get_evalnet", "get_evalnet_miou", "weights_from_keras", "load_evalnet", "evalnet_plan", "init_evalnet_weights"]
 
 
 class B200EvalNet:
@@ -51,6 +51,11 @@ class B200EvalNet:
 
     def get_weights(self):
         return [w.copy() for w in self._weights]
+
+    def save_weights(self, path):
+        """``.npz`` with the construction arguments + the weights in ``evalnet_plan`` order (read back by ``load_evalnet``)."""
+        arrs = {f"w{i:03d}": w for i, w in enumerate(self._weights)}
+        np.savez(path, __config__=np.array(repr(sorted(self.config.items()))), **arrs)
 
     def predict(self, x, batch_size=None, verbose=0, **_):
         """``model.predict([A, B])``: A uint8 [N,H,W,cA]; B [N,H,W,cB] -- integer 0/1 one-hot maps (functions.py:6004-6006,
@@ -141,3 +146,14 @@ def weights_from_keras(model):
     for l in a + b + trunk:
         ws += [np.asarray(w, np.float32) for w in l.get_weights()]
     return ws
+
+
+def load_evalnet(path, custom_objects=None, compile=False):
+    """Stand-in for ``tf.keras.models.load_model`` on an EvalNet ``.npz`` (``B200EvalNet.save_weights`` or
+    ``tools/export_keras_weights.py --evalnet``)."""
+    import ast
+    z = np.load(path, allow_pickle=False)
+    cfg = dict(ast.literal_eval(str(z["__config__"])))
+    n = len([k for k in z.files if k.startswith("w")])
+    return B200EvalNet(cfg["i_height"], cfg["i_width"], cfg["inputA_channels"], cfg["inputB_channels"], cfg["alpha"],
+                       [z[f"w{i:03d}"] for i in range(n)], cfg["n_heads"], cfg["ksi"], cfg["normalize_A"], cfg["normalize_B"])

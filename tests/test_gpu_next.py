@@ -459,3 +459,17 @@ def test_impp_driver_with_b200_evalnets(F, tmp_path):
         assert 1 <= c <= 5 and c == len([f for f in os.listdir(out / "masks") if f.startswith(f"s{i}___")])
         src = cv2.imread(str(root / "masks" / f"s{i}.png"), 0)
         assert np.array_equal(np.bincount(cv2.imread(str(out / "masks" / f"s{i}___0.png"), 0).ravel(), minlength=k), np.bincount(src.ravel(), minlength=k))
+
+
+def test_evalnet_save_load_roundtrip(tmp_path):
+    from inconsistencymasks_b200 import evalnet as EV
+    rng = np.random.default_rng(0)
+    m = EV.get_evalnet_miou(64, 64, 3, 5, 1.0, seed=3)
+    a = rng.integers(0, 256, size=(2, 64, 64, 3), dtype=np.uint8)
+    cls = rng.integers(0, 5, size=(2, 64, 64))
+    b = np.stack([(cls == k).astype(np.int32) for k in range(5)], axis=-1)
+    want = m.predict([a, b])
+    m.save_weights(str(tmp_path / "e.npz"))
+    m2 = EV.load_evalnet(str(tmp_path / "e.npz"))
+    got = m2.predict([a, b])
+    same(got[0], want[0]); same(got[1], want[1])
