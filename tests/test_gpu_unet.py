@@ -44,6 +44,8 @@ CASES = [
     (32, 32, 3, 1, 0.5, "sigmoid"),     # ISIC, alpha 0.5: widths 8..128 (fused engine: 8-channel maps as one plane, taps paired)
     (64, 48, 3, 1, 0.25, "sigmoid"),    # widths 4, 8, 16, ..: 8-channel planes on two levels, a 4-channel map inside one plane
     (64, 96, 1, 3, 0.5, "sigmoid"),     # grayscale + 8 channels: the input-block table feeds a single plane
+    (16, 16, 3, 1, 0.5, "sigmoid"),     # smallest legal input with 8-channel planes (2x2 / 1x1 maps at the bottom)
+    (208, 416, 3, 1, 0.5, "sigmoid"),   # 8-channel planes at the Cityscapes aspect (odd tile counts, pitch > 128: 4-D TMA boxes)
     (64, 48, 1, 3, 1.0, "sigmoid"),     # HeLa
     (32, 64, 3, 9, 2.0, "softmax"),     # SUIM noisy-student size: widths 32..512
     (48, 96, 3, 35, 1.0, "softmax"),    # Cityscapes aspect, K = 35
