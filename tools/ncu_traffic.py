@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """profiles/ncu_traffic.json from an `ncu --set full` capture of one trunk pass of the default bench shape:
 
-    ncu --set full --clock-control none -k regex:block_tc -c 8 -o gpurun_out/X/traffic python tools/trunk_probe.py --config isic --images 64 --passes 1 --engine fused
-    python tools/ncu_traffic.py gpurun_out/X/traffic.ncu-rep 64
+    ncu --set full --clock-control none -k regex:block_tc -c 8 -o gpurun_out/X/traffic python tools/trunk_probe.py --config isic --images 512 --passes 1 --engine fused
+    python tools/ncu_traffic.py gpurun_out/X/traffic.ncu-rep 512
 
 DRAM bytes (read + write) per image of every block-fused launch, keyed like bench.py's kernel rows ("block_front:0", ...),
 together with the digest of the sources the captured library was built from: bench.py reports `roofline.traffic` only when
@@ -25,6 +25,6 @@ for key, r in zip(keys, data):
     b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
     kernels[key] = dict(bytes_per_image=b / images, kernel=r[ik][:80])
 json.dump(dict(sources_digest=build.sources_digest(), capture=os.path.basename(rep), images=images, shape="ISIC 256x256x3, alpha 0.5 (default bench)",
-               note="captured at 64 images per launch: the 126 MB L2 still holds part of a launch's output when it ends (write-back not counted), so these are a LOWER bound for the 512-image launches of the bench; traffic above the algorithmic bytes would show re-reads, there are none",
+               note="capture at the launch size of the bench (512 images); at 64 images the 126 MB L2 still holds part of a launch's output when it ends and the figures come out ~2x lower",
                kernels=kernels), open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 print(json.dumps(kernels, indent=1))
