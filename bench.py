@@ -666,7 +666,7 @@ def main():
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--images-per-step", type=int, default=None)
     ap.add_argument("--e2e-images", type=int, default=None)
-    ap.add_argument("--e2e-chunk", type=int, default=512)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="images per chunk of the host pipeline; 0 = the library's default schedule")
     ap.add_argument("--im-images", type=int, default=512)
     ap.add_argument("--cpu-images", type=int, default=128)
     ap.add_argument("--ref-images-per-step", type=int, default=32)

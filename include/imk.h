@@ -212,6 +212,10 @@ int imk_ensemble_im_multiclass(imk_unet_t *const *nets, int M, const uint8_t *im
  *  that copies overlap compute, results are streamed back.  erode_kernel ==
  *  dilate_kernel == 0 only (the config.ini defaults); use the device-buffer calls
  *  for morphology.  Outputs as in the device calls above; any output may be NULL.
+ *  chunk > 0: images per chunk, as given.  chunk <= 0: the library picks -- up to
+ *  imk_max_chunk() images, at least four chunks, and a quarter and a half chunk at
+ *  both ends (the first upload and the last download are the only copies nothing
+ *  overlaps).  Results do not depend on the chunking.
  * ------------------------------------------------------------------------- */
 int imk_pseudo_label_binary_host(imk_unet_t *const *nets, int M, const uint8_t *images_host, int64_t N, int swap_rb,
                                  float thr, int strict_gt, int block_in, int block_out,

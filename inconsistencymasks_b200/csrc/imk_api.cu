@@ -200,18 +200,31 @@ int run_host_pipeline(imk_unet_t *const *nets, int M, bool multiclass, const uin
     const int K = d.num_outputmasks;
     const int planes = multiclass ? 1 : K;
     IMK_REQUIRE(!packed || HW % 8 == 0, "%s: the packed layout needs H*W to be a multiple of 8", who);
-    // default: large chunks (kernel efficiency), but at least four of them in flight through the three slots
-    if (chunk <= 0) chunk = std::min<int64_t>(kMaxChunk, std::max<int64_t>(64, (N + 3) / 4));
+    // default: large chunks (kernel efficiency), but at least four of them in flight through the three slots -- and a
+    // short ramp (a quarter and a half chunk) at both ends: the first upload and the last download are the only copies
+    // nothing overlaps, so they are made small.  An explicit chunk > 0 is used as given.
+    const bool auto_chunk = chunk <= 0;
+    if (auto_chunk) chunk = std::min<int64_t>(kMaxChunk, std::max<int64_t>(64, (N + 3) / 4));
     chunk = std::min<int64_t>(chunk, N);
+    std::vector<int64_t> sizes;
+    {
+        int64_t rest = N;
+        const bool ramp = auto_chunk && chunk >= 128 && N >= 4 * chunk;
+        if (ramp) { sizes.push_back(chunk / 4); sizes.push_back(chunk / 2); rest -= chunk / 4 + chunk / 2 + chunk / 2 + chunk / 4; }
+        for (; rest > 0; rest -= chunk) sizes.push_back(std::min<int64_t>(chunk, rest));
+        if (ramp) { sizes.push_back(chunk / 2); sizes.push_back(chunk / 4); }
+    }
     Pipeline &P = g_pipe;
     int rc = pipeline_reserve(P, chunk, (size_t)chunk * HW * d.in_channels, (size_t)chunk * HW, (size_t)chunk * HW * planes, planes);
     if (rc) return rc;
     // Each model keeps ONE workspace, so the kernels of consecutive chunks are issued to a single compute stream;
     // uploads and downloads run on their own streams, ordered by events.
-    const int64_t n_chunks = (N + chunk - 1) / chunk;
+    const int64_t n_chunks = (int64_t)sizes.size();
+    int64_t n_next = 0;
     for (int64_t i = 0; i < n_chunks; ++i) {
         Slot &S = P.slot[i % kSlots];
-        const int64_t n0 = i * chunk, n = std::min<int64_t>(chunk, N - n0);
+        const int64_t n0 = n_next, n = sizes[(size_t)i];
+        n_next += n;
         // the slot is free again once chunk i - kSlots has been downloaded
         if (i >= kSlots) IMK_CUDA(cudaStreamWaitEvent(P.up, S.down_done, 0));
         IMK_CUDA(cudaMemcpyAsync(S.img, images + n0 * HW * d.in_channels, (size_t)n * HW * d.in_channels, cudaMemcpyHostToDevice, P.up));

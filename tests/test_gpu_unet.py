@@ -340,6 +340,38 @@ def test_host_pipeline_multi_chunk_matches_single_calls(U, F):
     same(labels, ref.labels); same(im, ref.im); same(out, ref.image); same(sz, ref.im_size); same(pred, ref.pred_size)
 
 
+def test_host_pipeline_default_schedule_equals_fixed_chunks(U, F):
+    """chunk <= 0: the library's own schedule (quarter / half chunks at both ends, ragged middle) gives the bytes of a
+    fixed-chunk call, binary and multiclass."""
+    import ctypes as C
+    from inconsistencymasks_b200 import _lib
+    h, w, c, n = 16, 32, 1, 530
+    rng = np.random.default_rng(14)
+    images = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    _lib.check(_lib.lib.imk_set_max_chunk(128))
+    try:
+        for K, act in ((3, "sigmoid"), (4, "softmax")):
+            models = [U.B200UNet(h, w, c, K, 0.5, act, U.init_weights(c, K, 0.5, seed=700 + j)) for j in range(2)]
+            hs = (C.c_void_p * 2)(*[m.handle for m in models])
+            got = []
+            for chunk in (0, 128):
+                P = K if act == "sigmoid" else 1
+                labels = np.zeros((P, n, h, w), np.uint8); im = np.zeros((n, h, w), np.uint8)
+                out = np.zeros_like(images); sz = np.zeros(n, np.int64); pred = np.zeros((P, n), np.int64); eq = np.zeros(n, np.uint8)
+                if act == "sigmoid":
+                    _lib.check(_lib.lib.imk_pseudo_label_binary_host(hs, 2, images.ctypes.data, n, 0, 0.5, 0, 1, 1, out.ctypes.data,
+                                                                     labels.ctypes.data, im.ctypes.data, sz.ctypes.data, pred.ctypes.data, chunk))
+                else:
+                    _lib.check(_lib.lib.imk_pseudo_label_multiclass_host(hs, 2, images.ctypes.data, n, 0, 1, 1, out.ctypes.data,
+                                                                         labels.ctypes.data, im.ctypes.data, sz.ctypes.data, eq.ctypes.data, chunk))
+                got.append((labels, im, out, sz, pred, eq))
+            for x, y in zip(*got):
+                same(x, y)
+            assert got[0][1].any() and got[0][3].sum() > 0          # the masks are not trivially empty
+    finally:
+        _lib.check(_lib.lib.imk_set_max_chunk(0))
+
+
 def test_keras_like_surface(U, tmp_path):
     model = U.get_unet(32, 32, 3, 9, 1.0, "relu", "softmax", seed=3)
     assert model.input_shape == (None, 32, 32, 3) and model.output_shape == (None, 32, 32, 9)
